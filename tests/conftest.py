@@ -1,0 +1,78 @@
+"""pytest configuration: registers the `gpu` marker and shared helpers/fixtures."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: test needs a CUDA device (run on the B200 box)')
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+
+
+@pytest.fixture(scope='session')
+def ops_golden():
+    return load_golden('ops')
+
+
+# (fixture name) -> (config name, weight seed, [(maker, args)...]) ; mirrors tests/golden/make_golden.py
+FORWARD_CASES = {
+    'fwd_modelnet_b1': ('modelnet', 11, [('modelnet', (1000,))]),
+    'fwd_3dmatch_small_b1': ('3dmatch', 12, [('3dmatch', (2000, 3000))]),
+    'fwd_3dmatch_small_b2': ('3dmatch', 13, [('3dmatch', (2001, 2500)), ('3dmatch', (2002, 4000))]),
+}
+
+
+def make_case(name):
+    """Regenerate (cfg, state_dict, src_list, tgt_list) of a golden forward case from its seeds."""
+    from regtr_b200.config import get_config
+    from regtr_b200.synthetic import make_3dmatch_pair, make_modelnet_pair
+    from regtr_b200.weights import random_state_dict
+    cfg_name, wseed, makers = FORWARD_CASES[name]
+    cfg = get_config(cfg_name)
+    sd = random_state_dict(cfg, wseed)
+    pairs = [(make_modelnet_pair if kind == 'modelnet' else make_3dmatch_pair)(*args)
+             for kind, args in makers]
+    return cfg, sd, [p['src_xyz'] for p in pairs], [p['tgt_xyz'] for p in pairs]
+
+
+def check_forward_against_golden(out, meta, fx, n_pairs, feat_rtol, corr_atol, logit_atol, pose_atol,
+                                 exact_points=True):
+    """Shared comparison of a forward output dict (numpy-convertible) with a golden fixture."""
+    def npy(t):
+        return t.detach().cpu().numpy() if hasattr(t, 'detach') else np.asarray(t)
+    n_lvl = len(meta['points'])
+    for lvl in range(n_lvl):
+        assert np.array_equal(npy(meta['stack_lengths'][lvl]), fx[f'stack_lengths_{lvl}']), f'stack_lengths[{lvl}]'
+        for key in ('neighbors', 'pools', 'upsamples'):
+            got = npy(meta[key][lvl])
+            want = fx[f'{key}_{lvl}']
+            assert got.shape == want.shape, (key, lvl, got.shape, want.shape)
+            assert np.array_equal(got, want), f'{key}[{lvl}] indices differ'
+        if lvl > 0:
+            got, want = npy(meta['points'][lvl]), fx[f'points_{lvl}']
+            if exact_points:
+                assert np.array_equal(got, want), f'points[{lvl}] not bit-exact'
+            else:
+                np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
+    for b in range(n_pairs):
+        for side in ('src', 'tgt'):
+            fu, fc = npy(out[f'{side}_feat_un'][b]), npy(out[f'{side}_feat'][b])
+            s_un, s_c = float(fx[f'{side}_feat_un_{b}_absmax']), float(fx[f'{side}_feat_{b}_absmax'])
+            assert np.abs(fu[::7] - fx[f'{side}_feat_un_{b}_rows']).max() <= feat_rtol * s_un
+            assert np.abs(fc[:, ::7] - fx[f'{side}_feat_{b}_rows']).max() <= feat_rtol * s_c
+            assert abs(fu.astype(np.float64).sum() - float(fx[f'{side}_feat_un_{b}_sum'])) \
+                <= feat_rtol * s_un * fu.size ** 0.5 * 4
+            assert np.abs(npy(out[f'{side}_kp_warped'][b]) - fx[f'{side}_kp_warped_{b}']).max() <= corr_atol
+            assert np.abs(npy(out[f'{side}_overlap'][b]) - fx[f'{side}_overlap_{b}']).max() <= logit_atol
+    assert np.abs(npy(out['pose']) - fx['pose']).max() <= pose_atol

@@ -1,0 +1,172 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Every fixture is produced by the reference's own modules, imported through
+oracle/ref_bridge.py (third-party stubs per SURVEY.md Appendix A), on seeded
+inputs from regtr_b200.synthetic and seeded weights from regtr_b200.weights.
+Tests regenerate the same inputs/weights from the seeds and compare:
+  * `-m "not gpu"`: oracle (oracle/regtr_oracle.py) vs these fixtures  -> pins the oracle;
+  * `-m gpu`      : CUDA product vs these fixtures and vs the oracle.
+Fixtures are kept small: full integer metadata, but only a strided sample of the
+large float tensors plus their fp64 checksums.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_bridge  # noqa: E402
+from regtr_b200.config import get_config  # noqa: E402
+from regtr_b200.synthetic import make_3dmatch_pair, make_modelnet_pair  # noqa: E402
+from regtr_b200.weights import random_state_dict  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+# (fixture name, config, weight seed, list of pair makers)
+FORWARD_CASES = {
+    'fwd_modelnet_b1': ('modelnet', 11, [lambda: make_modelnet_pair(1000)]),
+    'fwd_3dmatch_small_b1': ('3dmatch', 12, [lambda: make_3dmatch_pair(2000, 3000)]),
+    'fwd_3dmatch_small_b2': ('3dmatch', 13, [lambda: make_3dmatch_pair(2001, 2500),
+                                             lambda: make_3dmatch_pair(2002, 4000)]),
+}
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def forward_fixture(name):
+    cfg_name, wseed, makers = FORWARD_CASES[name]
+    cfg = get_config(cfg_name)
+    sd = random_state_dict(cfg, wseed)
+    model = ref_bridge.build_reference_model(cfg, sd)
+    pairs = [mk() for mk in makers]
+    out = ref_bridge.reference_forward(model, [p['src_xyz'] for p in pairs], [p['tgt_xyz'] for p in pairs])
+    meta = out['kpconv_meta']
+    fx = {'pose': _np(out['pose'])}
+    for lvl in range(len(meta['points'])):
+        fx[f'stack_lengths_{lvl}'] = _np(meta['stack_lengths'][lvl]).astype(np.int64)
+        fx[f'neighbors_{lvl}'] = _np(meta['neighbors'][lvl]).astype(np.int32)
+        fx[f'pools_{lvl}'] = _np(meta['pools'][lvl]).astype(np.int32)
+        fx[f'upsamples_{lvl}'] = _np(meta['upsamples'][lvl]).astype(np.int32)
+        if lvl > 0:
+            fx[f'points_{lvl}'] = _np(meta['points'][lvl])
+    for b in range(len(pairs)):
+        for side in ('src', 'tgt'):
+            fx[f'{side}_kp_warped_{b}'] = _np(out[f'{side}_kp_warped'][b])
+            fx[f'{side}_overlap_{b}'] = _np(out[f'{side}_overlap'][b])
+            fu, fc = _np(out[f'{side}_feat_un'][b]), _np(out[f'{side}_feat'][b])
+            fx[f'{side}_feat_un_{b}_rows'] = fu[::7]
+            fx[f'{side}_feat_{b}_rows'] = fc[:, ::7]
+            fx[f'{side}_feat_un_{b}_sum'] = np.array(fu.astype(np.float64).sum())
+            fx[f'{side}_feat_{b}_sum'] = np.array(fc.astype(np.float64).sum())
+            fx[f'{side}_feat_un_{b}_absmax'] = np.array(np.abs(fu).max())
+            fx[f'{side}_feat_{b}_absmax'] = np.array(np.abs(fc).max())
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **fx)
+    print(name, {k: v.shape for k, v in fx.items() if k.startswith(('pose', 'stack'))})
+
+
+def op_fixtures():
+    """Small known-answer vectors for the individual reference ops on the hot path."""
+    m = ref_bridge.modules()
+    rng = np.random.default_rng(77)
+    fx = {}
+
+    # KPConv.forward (kpconv_blocks.py:269-414) incl. shadow neighbours and zero-sum rows
+    Nq, Ns, K, Cin, Cout, P = 37, 53, 11, 8, 12, 15
+    q = rng.normal(size=(Nq, 3)).astype(np.float32) * 0.1
+    s = rng.normal(size=(Ns, 3)).astype(np.float32) * 0.1
+    inds = rng.integers(0, Ns + 1, size=(Nq, K)).astype(np.int64)        # Ns == shadow
+    inds[3] = Ns                                                          # fully shadow row
+    x = rng.normal(size=(Ns, Cin)).astype(np.float32)
+    x[5] = -np.abs(x[5])                                                  # row with negative sum
+    conv = m.blocks.KPConv(P, 3, Cin, Cout, 0.12, 0.15, fixed_kernel_points='center',
+                           KP_influence='linear', aggregation_mode='sum')
+    W = rng.normal(size=(P, Cin, Cout)).astype(np.float32) * 0.3
+    kp = rng.normal(size=(P, 3)).astype(np.float32) * 0.08
+    kp[0] = 0
+    with torch.no_grad():
+        conv.weights.copy_(torch.from_numpy(W))
+        conv.kernel_points.copy_(torch.from_numpy(kp))
+        y = conv(torch.from_numpy(q), torch.from_numpy(s), torch.from_numpy(inds), torch.from_numpy(x))
+    fx.update(kp_q=q, kp_s=s, kp_inds=inds, kp_x=x, kp_W=W, kp_kp=kp, kp_extent=np.float32(0.12),
+              kp_out=_np(y))
+
+    # max_pool (127-143) and per-cloud InstanceNorm block (474-530)
+    with torch.no_grad():
+        fx['maxpool_out'] = _np(m.blocks.max_pool(torch.from_numpy(x), torch.from_numpy(inds)))
+        bn = m.blocks.BatchNormBlock(Cin, True, 0.02)
+        lens = torch.tensor([20, 33])
+        fx['inorm_lens'] = lens.numpy()
+        fx['inorm_out'] = _np(bn(torch.from_numpy(x), lens))
+
+    # PositionEmbeddingCoordsSine (position_embedding.py:7-50)
+    pe = m.posemb.PositionEmbeddingCoordsSine(3, 256, scale=1.0)
+    xyz = rng.normal(size=(29, 3)).astype(np.float32)
+    fx['pe_xyz'] = xyz
+    fx['pe_out'] = _np(pe(torch.from_numpy(xyz)))
+
+    # compute_rigid_transform (se3_torch.py:108-154), batched, incl. a reflection case
+    a = rng.normal(size=(4, 60, 3)).astype(np.float32)
+    R = np.stack([np.linalg.qr(rng.normal(size=(3, 3)))[0] for _ in range(4)]).astype(np.float32)
+    R[0] *= np.sign(np.linalg.det(R[0]))
+    R[1] *= -np.sign(np.linalg.det(R[1]))                                 # improper: exercises det fix
+    b = np.einsum('bij,bnj->bni', R, a) + rng.normal(size=(4, 1, 3)).astype(np.float32)
+    b += rng.normal(size=b.shape).astype(np.float32) * 0.01
+    w = rng.uniform(0, 1, size=(4, 60)).astype(np.float32)
+    w[2, :50] = 0
+    with torch.no_grad():
+        T = m.se3.compute_rigid_transform(torch.from_numpy(a), torch.from_numpy(b), torch.from_numpy(w))
+    fx.update(kabsch_a=a, kabsch_b=b, kabsch_w=w, kabsch_T=_np(T))
+
+    # TransformerCrossEncoder on a PADDED batch of 2 pairs (transformers.py:18-59, 183-244)
+    cfg = get_config('3dmatch')
+    sd = random_state_dict(cfg, 21)
+    layer = m.transformers.TransformerCrossEncoderLayer(
+        256, 8, 1024, 0.0, activation='relu', normalize_before=True,
+        sa_val_has_pos_emb=True, ca_val_has_pos_emb=True, attention_type='dot_prod')
+    enc = m.transformers.TransformerCrossEncoder(layer, 6, torch.nn.LayerNorm(256), return_intermediate=True)
+    enc.load_state_dict({k[len('transformer_encoder.'):]: v for k, v in sd.items()
+                         if k.startswith('transformer_encoder.')}, strict=True)
+    enc.eval()
+    S, T_ = [23, 17], [19, 31]
+    src = [torch.from_numpy(rng.normal(size=(n, 256)).astype(np.float32)) for n in S]
+    tgt = [torch.from_numpy(rng.normal(size=(n, 256)).astype(np.float32)) for n in T_]
+    sxyz = [torch.from_numpy(rng.normal(size=(n, 3)).astype(np.float32)) for n in S]
+    txyz = [torch.from_numpy(rng.normal(size=(n, 3)).astype(np.float32)) for n in T_]
+    pad = torch.nn.utils.rnn.pad_sequence
+
+    def mask(lens):
+        mk = torch.zeros((len(lens), max(lens)), dtype=torch.bool)
+        for i, l in enumerate(lens):
+            mk[i, l:] = True
+        return mk
+    with torch.no_grad():
+        so, to = enc(pad(src), pad(tgt), src_key_padding_mask=mask(S), tgt_key_padding_mask=mask(T_),
+                     src_pos=pad([pe(v) for v in sxyz]), tgt_pos=pad([pe(v) for v in txyz]))
+    for b in range(2):
+        fx[f'xenc_src_{b}'] = _np(src[b]); fx[f'xenc_tgt_{b}'] = _np(tgt[b])
+        fx[f'xenc_sxyz_{b}'] = _np(sxyz[b]); fx[f'xenc_txyz_{b}'] = _np(txyz[b])
+        fx[f'xenc_src_out_{b}'] = _np(so[:, :S[b], b]); fx[f'xenc_tgt_out_{b}'] = _np(to[:, :T_[b], b])
+    np.savez_compressed(os.path.join(OUT, 'ops.npz'), **fx)
+    print('ops', len(fx), 'arrays')
+
+
+if __name__ == '__main__':
+    torch.manual_seed(0)
+    np.random.seed(0)
+    op_fixtures()
+    for case in FORWARD_CASES:
+        forward_fixture(case)
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith('.npz'):
+            print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, 'KiB')

@@ -1,0 +1,91 @@
+"""CPU tests: the oracle restatement vs the golden fixtures produced by the unmodified
+reference (tests/golden/make_golden.py).  These pin oracle/ -- they never touch the GPU."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import FORWARD_CASES, check_forward_against_golden, load_golden, make_case
+from oracle import pre, regtr_oracle as O
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_kpconv_matches_reference(ops_golden):
+    g = ops_golden
+    y = O.kpconv(T(g['kp_q']), T(g['kp_s']), T(g['kp_inds']), T(g['kp_x']), T(g['kp_W']), T(g['kp_kp']),
+                 float(g['kp_extent']))
+    assert np.abs(y.numpy() - g['kp_out']).max() <= 1e-5 * np.abs(g['kp_out']).max()
+    assert np.all(y.numpy()[3] == 0)          # fully-shadow row -> zeros / max(1, 0)
+
+
+def test_maxpool_instnorm_posemb_match_reference(ops_golden):
+    g = ops_golden
+    assert np.array_equal(O.max_pool(T(g['kp_x']), T(g['kp_inds'])).numpy(), g['maxpool_out'])
+    np.testing.assert_allclose(O.instance_norm(T(g['kp_x']), g['inorm_lens']).numpy(), g['inorm_out'],
+                               rtol=0, atol=2e-6)
+    np.testing.assert_allclose(O.pos_embed_sine(T(g['pe_xyz'])).numpy(), g['pe_out'], rtol=0, atol=1e-6)
+
+
+def test_kabsch_matches_reference(ops_golden):
+    g = ops_golden
+    Tm = O.kabsch(T(g['kabsch_a']), T(g['kabsch_b']), T(g['kabsch_w'])).numpy()
+    np.testing.assert_allclose(Tm, g['kabsch_T'], rtol=0, atol=2e-5)
+    R = Tm[..., :3]
+    assert np.all(np.linalg.det(R) > 0.999)   # det fix active on the improper case
+
+
+def test_cross_encoder_unpadded_equals_reference_padded(ops_golden):
+    from regtr_b200.config import get_config
+    from regtr_b200.weights import random_state_dict
+    g = ops_golden
+    cfg = get_config('3dmatch')
+    sd = random_state_dict(cfg, 21)
+    for b in range(2):
+        so, to = O.cross_encoder(sd, cfg, T(g[f'xenc_src_{b}']), T(g[f'xenc_tgt_{b}']),
+                                 O.pos_embed_sine(T(g[f'xenc_sxyz_{b}'])), O.pos_embed_sine(T(g[f'xenc_txyz_{b}'])))
+        np.testing.assert_allclose(so.numpy(), g[f'xenc_src_out_{b}'], rtol=0, atol=3e-5)
+        np.testing.assert_allclose(to.numpy(), g[f'xenc_tgt_out_{b}'], rtol=0, atol=3e-5)
+
+
+@pytest.mark.parametrize('case', sorted(FORWARD_CASES))
+def test_forward_matches_reference(case):
+    cfg, sd, src, tgt = make_case(case)
+    fx = load_golden(case)
+    out = O.forward(sd, cfg, src, tgt)
+    check_forward_against_golden(out, out['kpconv_meta'], fx, len(src), feat_rtol=2e-5, corr_atol=3e-5,
+                                 logit_atol=5e-5, pose_atol=1e-4)   # north_star: pose within 1e-4
+
+
+def test_c_preprocess_matches_numpy_twin():
+    rng = np.random.default_rng(5)
+    pts = rng.uniform(-0.3, 0.3, size=(700, 3)).astype(np.float32)
+    pts[:50] = np.round(pts[:50] / 0.05) * 0.05           # points exactly on voxel faces
+    lens = np.array([300, 0, 400], dtype=np.int64)        # includes an empty cloud
+    sub_c, len_c = pre.grid_subsample(pts, lens, 0.05)
+    sub_n, len_n = pre.grid_subsample_np(pts, lens, 0.05)
+    assert np.array_equal(len_c, len_n) and np.array_equal(sub_c, sub_n)
+    nb_c = pre.ball_query(sub_c, len_c, pts, lens, 9, 0.07)
+    nb_n = pre.ball_query_np(sub_c, len_c, pts, lens, 9, 0.07)
+    assert np.array_equal(nb_c, nb_n)
+    assert nb_c.max() == len(pts)                          # padding value = total supports
+
+
+def test_refcpp_cross_check_level_sizes():
+    """Reference C++ core (oracle/_ref) agrees with the oracle on what it can agree on:
+    the SET of neighbours when nothing is truncated, and similar level sizes."""
+    if not pre.RefCpp.available():
+        pytest.skip('oracle/_ref not built (needs /root/reference at build time)')
+    ref = pre.RefCpp()
+    rng = np.random.default_rng(9)
+    pts = rng.uniform(-0.5, 0.5, size=(900, 3)).astype(np.float32)
+    lens = np.array([400, 500])
+    K = 64
+    a = pre.ball_query(pts, lens, pts, lens, K, 0.11)
+    b = ref.batch_neighbors(pts, pts, lens, lens, 0.11, K)
+    assert (a < len(pts)).sum(1).max() < K                 # nothing truncated in this case
+    assert all(set(x[x < len(pts)]) == set(y[y < len(pts)]) for x, y in zip(a, b))
+    sub_o, len_o = pre.grid_subsample(pts, lens, 0.1)
+    sub_r, len_r = ref.batch_subsample(pts, lens, 0.1)
+    assert np.abs(len_o - len_r).max() <= 0.05 * len_o.max()
