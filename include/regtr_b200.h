@@ -1,0 +1,165 @@
+/*
+ * regtr_b200 -- C ABI of the B200-native RegTR correspondence-prediction hot path.
+ *
+ * The reference (yewzijian/RegTR) has no FFI layer: its boundary for this path is
+ * the nn.Module surface (src/models/regtr.py:104-235) over ATen ops plus two
+ * un-vendored CUDA libraries.  Each entry point below replaces one reference
+ * operation (file:line cited per function; paths relative to /root/reference/src).
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless marked "host";
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no
+ *     call synchronises, allocates or frees (workspaces are caller-owned and sized
+ *     by the matching *_ws_bytes function);
+ *   - stacked clouds are described by int32 prefix offsets `offs[n_clouds + 1]`
+ *     (device memory) so that data-dependent level sizes never cross to the host
+ *     inside the pyramid; `*_cap` arguments are host-known capacities (upper
+ *     bounds of offs[n_clouds]) used only to size grids and buffers;
+ *   - return value: 0 on success, REGTR_ERR_* (<0) on a rejected argument,
+ *     -(1000 + cudaError_t) when a launch fails.  Data-dependent failures
+ *     (coordinates outside the +-32767-cell key range) are reported through the
+ *     device status word, see regtr_status_*.
+ */
+#ifndef REGTR_B200_H_
+#define REGTR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REGTR_OK 0
+#define REGTR_ERR_ARG (-1)        /* null pointer / negative size / unsupported shape */
+#define REGTR_ERR_WORKSPACE (-2)  /* workspace too small */
+#define REGTR_ERR_UNSUPPORTED (-3)
+#define REGTR_ERR_CUBLAS (-4)
+
+#define REGTR_STATUS_KEY_RANGE 1u /* a voxel / cell coordinate left the 16-bit key range */
+
+int regtr_version(void);                 /* ABI version, currently 1 */
+const char* regtr_build_info(void);      /* host pointer: arch + compile flags string */
+
+/* ---- pyramid pre-processing ------------------------------------------------------- */
+
+/* Voxel-grid barycentre sub-sampling.
+ * Replaces batch_grid_subsampling_kpconv_gpu (models/backbone_kpconv/kpconv.py:213-240,
+ * i.e. MinkowskiEngine 0.5.4 SparseTensor(UNWEIGHTED_AVERAGE)) with the deterministic
+ * rules of DESIGN.md: voxel = floor(p / dl) (IEEE fp32 division), output ordered by
+ * ascending (cloud, vx, vy, vz), barycentre = fp32 sum in ascending input index / count.
+ * xyz (n_cap,3) f32; offs (n_clouds+1) i32; out_xyz (n_cap,3); out_offs (n_clouds+1).
+ * status: device uint32 word, OR-ed with REGTR_STATUS_* on data-dependent errors. */
+size_t regtr_grid_subsample_ws_bytes(int n_cap);
+int regtr_grid_subsample(const float* xyz, const int32_t* offs, int n_clouds, int n_cap, float dl,
+                         float* out_xyz, int32_t* out_offs, uint32_t* status,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* Uniform cell list over a stacked point set (search structure for regtr_ball_query).
+ * `grid` is an opaque caller-owned buffer of regtr_cellgrid_bytes(n_cap) bytes; `order`
+ * (n_cap) i32, optional, receives the cell-sorted permutation of the points (a spatially
+ * coherent processing order for queries drawn from the same set). */
+size_t regtr_cellgrid_bytes(int n_cap);
+size_t regtr_cellgrid_ws_bytes(int n_cap);
+int regtr_cellgrid_build(const float* xyz, const int32_t* offs, int n_clouds, int n_cap, float cell,
+                         void* grid, int32_t* order, uint32_t* status,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* Fixed-radius neighbour search, first K supports in ascending index order.
+ * Replaces batch_neighbors_kpconv_gpu (kpconv.py:261-288: pytorch3d 0.6.0 packed_to_padded +
+ * ball_query + re-packing): per query keep support j (ascending) while
+ * ((dx*dx + dy*dy) + dz*dz) < r*r in fp32 without FMA contraction; pad with the total
+ * support count.  `s_grid` must have been built over (s, s_offs) with capacity s_cap and
+ * cell >= radius.
+ * q_order (optional, nq_cap): processing order of the queries.  out_idx32 / out_idx64
+ * (nq_cap,K): either may be NULL. */
+int regtr_ball_query(const float* q, const int32_t* q_offs, const int32_t* q_order,
+                     const float* s, const int32_t* s_offs, const void* s_grid,
+                     int n_clouds, int nq_cap, int s_cap, int K, float radius,
+                     int32_t* out_idx32, int64_t* out_idx64, void* stream);
+
+/* ---- KPConv encoder --------------------------------------------------------------- */
+
+/* Rigid KPConv, linear influence, 'sum' aggregation.
+ * Replaces KPConv.forward (models/backbone_kpconv/kpconv_blocks.py:269-414):
+ *   out[n] = (1/max(1,#{k: sum_c x[idx[n,k]] > 0})) * sum_p (sum_k h(n,k,p) x[idx[n,k]]) W[p]
+ *   h = max(0, 1 - |s[idx[n,k]] - q[n] - kp[p]| / extent); idx == Ns is the shadow neighbour.
+ * q (Nq,3) s (Ns,3) idx (Nq,K) i32, x (Ns,Cin) f32, W (P,Cin,Cout) f32, kp (P,3), out (Nq,Cout).
+ * P must be 15.  Cin in {1..16} or a multiple of 32 up to 256.
+ * ws: regtr_kpconv_ws_bytes(Nq, Ns, Cin) bytes (aggregated features + row flags). */
+size_t regtr_kpconv_ws_bytes(int Nq, int Ns, int Cin);
+int regtr_kpconv_fwd(const float* q, const float* s, const int32_t* idx, const float* x,
+                     const float* W, const float* kp, int Nq, int Ns, int K, int Cin, int Cout,
+                     float extent, float* out, void* ws, size_t ws_bytes, void* stream);
+
+/* Gather + influence + aggregation stage alone: wf (Nq, 15*Cin), already divided by the
+ * neighbour count.  (The HBM-bound "neighbour gather" kernel of the north star.) */
+int regtr_kpconv_aggregate(const float* q, const float* s, const int32_t* idx, const float* x,
+                           const float* kp, int Nq, int Ns, int K, int Cin, float extent,
+                           float* wf, uint8_t* rowflag_ws, void* stream);
+
+/* max over the K gathered rows with a zero shadow row.  Replaces max_pool
+ * (kpconv_blocks.py:127-143).  x (Ns,C), idx (Nq,K) i32 -> out (Nq,C). */
+int regtr_max_pool(const float* x, const int32_t* idx, int Nq, int Ns, int K, int C, float* out,
+                   void* stream);
+
+/* Per-cloud InstanceNorm1d(affine=False, eps) over the points of each cloud, optional
+ * residual add, optional LeakyReLU.  Replaces BatchNormBlock.forward + nn.LeakyReLU
+ * (kpconv_blocks.py:497-519, 546-561, 646, 741):  out = act(norm(x) + res).
+ * x (n,C); offs (n_clouds+1) i32 device; n_cap >= offs[n_clouds]; res optional (n,C);
+ * slope < 0 disables the activation.  In-place (out == x) is allowed. */
+size_t regtr_instnorm_ws_bytes(int n_cap, int n_clouds, int C);
+int regtr_instnorm_act(const float* x, const int32_t* offs, int n_clouds, int n_cap, int C, float eps,
+                       const float* res, float slope, float* out, void* ws, size_t ws_bytes,
+                       void* stream);
+
+/* ---- transformer ------------------------------------------------------------------ */
+
+/* 3-D sine position embedding.  Replaces PositionEmbeddingCoordsSine.forward
+ * (models/transformer/position_embedding.py:29-50).  dim_t (n_freq) f32 is the reference's
+ * `temperature ** (2*(i//2)/n_freq)` table; out (n, d_model), zero padded. */
+int regtr_pos_embed_sine(const float* xyz, int n, const float* dim_t, int n_freq, int d_model,
+                         float scale, float* out, void* stream);
+
+/* LayerNorm over the last dim with optional position add:  y = LN(x)*g + b ;
+ * y_pos = y + pos.  Replaces nn.LayerNorm + with_pos_embed (transformers.py:117-119,
+ * 194-196, 213-215, 232).  Any of y / y_pos may be NULL. */
+int regtr_layernorm_pos(const float* x, const float* gamma, const float* beta, const float* pos,
+                        int n, int E, float eps, float* y, float* y_pos, void* stream);
+
+/* Variable-length multi-head attention core, fp32:  O = softmax(Q K^T * scale) V per head.
+ * Replaces the attention core of nn.MultiheadAttention as called at
+ * transformers.py:197-226 (key-padding masks become explicit (start,len) ranges).
+ * Problem i attends queries rows [q_start[i], q_start[i]+q_len[i]) of Q to key rows
+ * [k_start[i], k_start[i]+k_len[i]) of K/V.  Q/K/V/O are row-major with leading
+ * dimensions ldq/ldk/ldv/ldo (floats); head h uses columns [h*head_dim, (h+1)*head_dim).
+ * head_dim must be 32.  max_q_len: host upper bound of q_len[]. */
+int regtr_mha_varlen_fwd(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
+                         float* O, int ldo, const int32_t* q_start, const int32_t* q_len,
+                         const int32_t* k_start, const int32_t* k_len, int n_problems,
+                         int max_q_len, int n_heads, int head_dim, float scale, void* stream);
+
+/* ---- pose ------------------------------------------------------------------------- */
+
+/* Weighted Kabsch.  Replaces compute_rigid_transform (utils/se3_torch.py:108-154):
+ * problem i uses rows [offs[i], offs[i+1]) of a,b (n,3) and w (n); T (n_problems,3,4),
+ * T*a = b.  One warp per problem, fp64 accumulation, one-sided Jacobi 3x3 SVD. */
+int regtr_kabsch_fwd(const float* a, const float* b, const float* w, const int32_t* offs,
+                     int n_problems, float* T, void* stream);
+
+/* Fused correspondence assembly + sigmoid + Kabsch for RegTR.forward (models/regtr.py:185-203):
+ * kp (n,3) coarse key points, packed src clouds first then tgt clouds; corr (L,n,3) predicted
+ * correspondences; logit (L,n) overlap logits; offs (2B+1) i32 cloud offsets.
+ * pose (L,B,3,4): for pair b, a=[src_kp ; tgt_corr], b=[src_corr ; tgt_kp],
+ * w=[sigmoid(src_logit) ; sigmoid(tgt_logit)]. */
+int regtr_pose_from_corr(const float* kp, const float* corr, const float* logit,
+                         const int32_t* offs, int n, int B, int L, float* pose, void* stream);
+
+/* ---- status word helpers (device uint32) ------------------------------------------ */
+int regtr_status_clear(uint32_t* status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REGTR_B200_H_ */

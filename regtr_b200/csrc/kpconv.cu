@@ -1,0 +1,348 @@
+// KPConv encoder kernels: neighbour gather + kernel-point influence + aggregation
+// (the HBM-bound "gather" of the north star), max-pool gather, and the
+// [Nq, 15*Cin] x [15*Cin, Cout] weight contraction.
+//
+// Reference behaviour replaced (paths relative to /root/reference/src):
+//   models/backbone_kpconv/kpconv_blocks.py:269-414  KPConv.forward (rigid, linear, sum)
+//   models/backbone_kpconv/kpconv_blocks.py:127-143  max_pool
+#include <cublas_v2.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int KP = 15;          // kernel points (config num_kernel_points)
+constexpr int KPP = 16;         // padded
+constexpr int AGG_WARPS = 8;
+
+// flags[r] = (sum_c x[r,c] > 0): the reference counts a neighbour only when its feature
+// row sums to a positive number (kpconv_blocks.py:409-412).  Summed in fp64 so that the
+// sign is the mathematically exact one whenever |sum| is above fp32 rounding noise.
+__global__ void k_row_flags(const float* __restrict__ x, int n, int C, uint8_t* __restrict__ flags) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    double acc = 0.0;
+    for (int c = lane; c < C; c += 32) acc += (double)x[(size_t)warp * C + c];
+    acc = warp_sum(acc);
+    if (lane == 0) flags[warp] = acc > 0.0;
+}
+
+__device__ __forceinline__ void influences(float rx, float ry, float rz, const float* __restrict__ kp_s,
+                                           float inv_dummy, float extent, float* __restrict__ w) {
+    (void)inv_dummy;
+#pragma unroll
+    for (int p = 0; p < KP; ++p) {
+        const float dx = rx - kp_s[3 * p + 0], dy = ry - kp_s[3 * p + 1], dz = rz - kp_s[3 * p + 2];
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        w[p] = fmaxf(0.f, 1.f - sqrtf(d2) / extent);
+    }
+}
+
+// Phase 1 shared by both aggregation kernels: lanes own neighbours, compute the 15
+// influences, compact the valid (non-shadow) neighbours into shared memory.
+// Returns (n_valid, neighbour_count) to every lane.
+__device__ __forceinline__ void stage_neighbours(const float* __restrict__ s, const int32_t* __restrict__ idx_row,
+                                                 const uint8_t* __restrict__ flags, const float* __restrict__ kp_s,
+                                                 float qx, float qy, float qz, int Ns, int K, float extent,
+                                                 float* __restrict__ w_s, int* __restrict__ id_s, int lane,
+                                                 int& n_valid, int& n_counted) {
+    int base = 0, counted = 0;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int kk = k0 + lane;
+        int id = Ns;
+        if (kk < K) id = idx_row[kk];
+        const bool valid = (id >= 0) && (id < Ns);
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            float w[KP];
+            influences(s[3 * id + 0] - qx, s[3 * id + 1] - qy, s[3 * id + 2] - qz, kp_s, 0.f, extent, w);
+            float4* dst = reinterpret_cast<float4*>(w_s + pos * KPP);
+            dst[0] = make_float4(w[0], w[1], w[2], w[3]);
+            dst[1] = make_float4(w[4], w[5], w[6], w[7]);
+            dst[2] = make_float4(w[8], w[9], w[10], w[11]);
+            dst[3] = make_float4(w[12], w[13], w[14], 0.f);
+            id_s[pos] = id;
+            counted += flags[id];
+        }
+        base += __popc(m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, o);
+    __syncwarp();
+    n_valid = base;
+    n_counted = counted;
+}
+
+// Cin multiple of 32: lane owns VEC channels; per valid neighbour one coalesced row load
+// and 15*VEC FMAs against influences broadcast from shared memory.
+template <int VEC, int UNROLL>
+__global__ void __launch_bounds__(AGG_WARPS * 32)
+k_kpconv_agg(const float* __restrict__ q, const float* __restrict__ s, const int32_t* __restrict__ idx,
+             const float* __restrict__ x, const uint8_t* __restrict__ flags, const float* __restrict__ kp,
+             int Nq, int Ns, int K, float extent, float* __restrict__ wf) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int CIN = VEC * 32;
+    constexpr int NV4 = VEC >= 4 ? VEC / 4 : 1;          // float4 loads per lane
+    float* kp_s = reinterpret_cast<float*>(smem_raw);     // 48 floats
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Kp = (K + 3) & ~3;
+    float* w_s = kp_s + 48 + warp * (Kp * KPP);
+    int* id_s = reinterpret_cast<int*>(kp_s + 48 + AGG_WARPS * (Kp * KPP)) + warp * Kp;
+    if (threadIdx.x < 3 * KP) kp_s[threadIdx.x] = kp[threadIdx.x];
+    __syncthreads();
+    const int qi = blockIdx.x * AGG_WARPS + warp;
+    if (qi >= Nq) return;
+
+    int n_valid, n_counted;
+    stage_neighbours(s, idx + (size_t)qi * K, flags, kp_s, q[3 * qi], q[3 * qi + 1], q[3 * qi + 2], Ns, K, extent,
+                     w_s, id_s, lane, n_valid, n_counted);
+
+    float acc[KP][VEC];
+#pragma unroll
+    for (int p = 0; p < KP; ++p)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[p][v] = 0.f;
+
+    for (int k0 = 0; k0 < n_valid; k0 += UNROLL) {
+        float xv[UNROLL][VEC];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int kk = min(k0 + u, n_valid - 1);
+            const float* row = x + (size_t)id_s[kk] * CIN;
+            if constexpr (VEC == 1) {
+                xv[u][0] = __ldg(row + lane);
+            } else if constexpr (VEC == 2) {
+                const float2 t = __ldg(reinterpret_cast<const float2*>(row) + lane);
+                xv[u][0] = t.x; xv[u][1] = t.y;
+            } else {
+#pragma unroll
+                for (int j = 0; j < NV4; ++j) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(row) + j * 32 + lane);
+                    xv[u][4 * j + 0] = t.x; xv[u][4 * j + 1] = t.y; xv[u][4 * j + 2] = t.z; xv[u][4 * j + 3] = t.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (k0 + u < n_valid) {
+                const float4* wr = reinterpret_cast<const float4*>(w_s + (k0 + u) * KPP);
+                const float4 a = wr[0], b = wr[1], c = wr[2], d = wr[3];
+                const float w[KP] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z};
+#pragma unroll
+                for (int p = 0; p < KP; ++p)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) acc[p][v] = fmaf(w[p], xv[u][v], acc[p][v]);
+            }
+        }
+    }
+
+    const float inv = 1.f / (float)max(n_counted, 1);
+    float* out = wf + (size_t)qi * (KP * CIN);
+#pragma unroll
+    for (int p = 0; p < KP; ++p) {
+        if constexpr (VEC == 1) {
+            out[p * CIN + lane] = acc[p][0] * inv;
+        } else if constexpr (VEC == 2) {
+            reinterpret_cast<float2*>(out + p * CIN)[lane] = make_float2(acc[p][0] * inv, acc[p][1] * inv);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NV4; ++j)
+                reinterpret_cast<float4*>(out + p * CIN)[j * 32 + lane] =
+                    make_float4(acc[p][4 * j] * inv, acc[p][4 * j + 1] * inv, acc[p][4 * j + 2] * inv,
+                                acc[p][4 * j + 3] * inv);
+        }
+    }
+}
+
+// Small Cin (1..16): lanes own neighbours all the way, channel sums by warp shuffle.
+__global__ void __launch_bounds__(AGG_WARPS * 32)
+k_kpconv_agg_small(const float* __restrict__ q, const float* __restrict__ s, const int32_t* __restrict__ idx,
+                   const float* __restrict__ x, const uint8_t* __restrict__ flags, const float* __restrict__ kp,
+                   int Nq, int Ns, int K, int Cin, float extent, float* __restrict__ wf) {
+    __shared__ float kp_s[48];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 3 * KP) kp_s[threadIdx.x] = kp[threadIdx.x];
+    __syncthreads();
+    const int qi = blockIdx.x * AGG_WARPS + warp;
+    if (qi >= Nq) return;
+    const float qx = q[3 * qi], qy = q[3 * qi + 1], qz = q[3 * qi + 2];
+    float* out = wf + (size_t)qi * (KP * Cin);
+    int counted = 0;
+    for (int c = 0; c < Cin; ++c) {
+        float accp[KP];
+#pragma unroll
+        for (int p = 0; p < KP; ++p) accp[p] = 0.f;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const int kk = k0 + lane;
+            int id = Ns;
+            if (kk < K) id = idx[(size_t)qi * K + kk];
+            if (id >= 0 && id < Ns) {
+                float w[KP];
+                influences(s[3 * id] - qx, s[3 * id + 1] - qy, s[3 * id + 2] - qz, kp_s, 0.f, extent, w);
+                const float xv = x[(size_t)id * Cin + c];
+#pragma unroll
+                for (int p = 0; p < KP; ++p) accp[p] = fmaf(w[p], xv, accp[p]);
+                if (c == 0) counted += flags[id];
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < KP; ++p) accp[p] = warp_sum(accp[p]);
+        if (c == 0) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, o);
+        }
+        const float inv = 1.f / (float)max(counted, 1);
+        if (lane < KP) {
+            float v = 0.f;
+#pragma unroll
+            for (int p = 0; p < KP; ++p) v = (lane == p) ? accp[p] : v;
+            out[lane * Cin + c] = v * inv;
+        }
+    }
+}
+
+// out[q, c] = max(0-shadow, x[idx[q,k], c]) ; 4 channels per thread.
+__global__ void k_max_pool(const float* __restrict__ x, const int32_t* __restrict__ idx, int Nq, int Ns, int K, int C,
+                           float* __restrict__ out) {
+    const int c4 = C >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)Nq * c4) return;
+    const int qi = (int)(t / c4), cc = (int)(t % c4);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int k = 0; k < K; ++k) {
+        const int id = idx[(size_t)qi * K + k];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (id >= 0 && id < Ns) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)id * C) + cc);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+    reinterpret_cast<float4*>(out + (size_t)qi * C)[cc] = m;
+}
+
+__global__ void k_max_pool_scalar(const float* __restrict__ x, const int32_t* __restrict__ idx, int Nq, int Ns, int K,
+                                  int C, float* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)Nq * C) return;
+    const int qi = (int)(t / C), c = (int)(t % C);
+    float m = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+        const int id = idx[(size_t)qi * K + k];
+        m = fmaxf(m, (id >= 0 && id < Ns) ? x[(size_t)id * C + c] : 0.f);
+    }
+    out[(size_t)qi * C + c] = m;
+}
+
+// ---- cuBLAS handle (one per device, created on first use)
+std::mutex g_mu;
+cublasHandle_t g_handles[64] = {};
+
+cublasHandle_t get_handle() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!g_handles[dev]) {
+        if (cublasCreate(&g_handles[dev]) != CUBLAS_STATUS_SUCCESS) return nullptr;
+        cublasSetMathMode(g_handles[dev], CUBLAS_PEDANTIC_MATH);   // fp32 parity path: no TF32
+    }
+    return g_handles[dev];
+}
+
+size_t agg_smem_bytes(int K) {
+    const int Kp = (K + 3) & ~3;
+    return sizeof(float) * 48 + (size_t)AGG_WARPS * Kp * (KPP * sizeof(float) + sizeof(int));
+}
+
+template <int VEC, int UNROLL>
+int launch_agg(const float* q, const float* s, const int32_t* idx, const float* x, const uint8_t* flags,
+               const float* kp, int Nq, int Ns, int K, float extent, float* wf, cudaStream_t st) {
+    const size_t smem = agg_smem_bytes(K);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_kpconv_agg<VEC, UNROLL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return -(1000 + (int)e);
+    }
+    k_kpconv_agg<VEC, UNROLL><<<regtr_cdiv(Nq, AGG_WARPS), AGG_WARPS * 32, smem, st>>>(q, s, idx, x, flags, kp, Nq, Ns,
+                                                                                     K, extent, wf);
+    REGTR_CHECK_LAUNCH();
+    return REGTR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t regtr_kpconv_ws_bytes(int Nq, int Ns, int Cin) {
+    return regtr_align(sizeof(float) * (size_t)(Nq > 0 ? Nq : 1) * KP * (size_t)Cin) +
+           regtr_align((size_t)(Ns > 0 ? Ns : 1));
+}
+
+int regtr_kpconv_aggregate(const float* q, const float* s, const int32_t* idx, const float* x, const float* kp,
+                           int Nq, int Ns, int K, int Cin, float extent, float* wf, uint8_t* rowflag_ws,
+                           void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (Nq < 0 || Ns < 0 || K <= 0 || K > 128 || Cin <= 0 || !(extent > 0.f)) return REGTR_ERR_ARG;
+    if (!(Cin <= 16 || (Cin % 32 == 0 && Cin <= 256 && (Cin / 32 == 1 || Cin / 32 == 2 || Cin / 32 == 4 || Cin / 32 == 8))))
+        return REGTR_ERR_UNSUPPORTED;
+    if (Nq == 0) return REGTR_OK;
+    if (!q || !s || !idx || !x || !kp || !wf || !rowflag_ws) return REGTR_ERR_ARG;
+    if (Ns > 0) {
+        k_row_flags<<<regtr_cdiv((long long)Ns * 32, 256), 256, 0, st>>>(x, Ns, Cin, rowflag_ws);
+        REGTR_CHECK_LAUNCH();
+    }
+    if (Cin <= 16) {
+        k_kpconv_agg_small<<<regtr_cdiv(Nq, AGG_WARPS), AGG_WARPS * 32, 0, st>>>(q, s, idx, x, rowflag_ws, kp, Nq, Ns,
+                                                                                K, Cin, extent, wf);
+        REGTR_CHECK_LAUNCH();
+        return REGTR_OK;
+    }
+    switch (Cin / 32) {
+        case 1: return launch_agg<1, 4>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, K, extent, wf, st);
+        case 2: return launch_agg<2, 4>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, K, extent, wf, st);
+        case 4: return launch_agg<4, 4>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, K, extent, wf, st);
+        case 8: return launch_agg<8, 2>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, K, extent, wf, st);
+    }
+    return REGTR_ERR_UNSUPPORTED;
+}
+
+int regtr_kpconv_fwd(const float* q, const float* s, const int32_t* idx, const float* x, const float* W,
+                     const float* kp, int Nq, int Ns, int K, int Cin, int Cout, float extent, float* out, void* ws,
+                     size_t ws_bytes, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (Cout <= 0 || Cin <= 0 || Nq < 0 || Ns < 0) return REGTR_ERR_ARG;
+    if (Nq == 0) return REGTR_OK;
+    if (!W || !out || !ws) return REGTR_ERR_ARG;
+    if (ws_bytes < regtr_kpconv_ws_bytes(Nq, Ns, Cin)) return REGTR_ERR_WORKSPACE;
+    float* wf = (float*)ws;
+    uint8_t* flags = (uint8_t*)ws + regtr_align(sizeof(float) * (size_t)Nq * KP * (size_t)Cin);
+    int rc = regtr_kpconv_aggregate(q, s, idx, x, kp, Nq, Ns, K, Cin, extent, wf, flags, stream_);
+    if (rc != REGTR_OK) return rc;
+    // out[Nq,Cout] = wf[Nq,15*Cin] @ W[15*Cin,Cout]  (row-major)  ==  column-major out^T = W^T wf^T
+    cublasHandle_t h = get_handle();
+    if (!h) return REGTR_ERR_CUBLAS;
+    if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) return REGTR_ERR_CUBLAS;
+    const float one = 1.f, zero = 0.f;
+    const int KD = KP * Cin;
+    if (cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, Cout, Nq, KD, &one, W, Cout, wf, KD, &zero, out, Cout) !=
+        CUBLAS_STATUS_SUCCESS)
+        return REGTR_ERR_CUBLAS;
+    return REGTR_OK;
+}
+
+int regtr_max_pool(const float* x, const int32_t* idx, int Nq, int Ns, int K, int C, float* out, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (Nq < 0 || Ns < 0 || K <= 0 || C <= 0) return REGTR_ERR_ARG;
+    if (Nq == 0) return REGTR_OK;
+    if (!x || !idx || !out) return REGTR_ERR_ARG;
+    if (C % 4 == 0) {
+        k_max_pool<<<regtr_cdiv((long long)Nq * (C / 4), 256), 256, 0, st>>>(x, idx, Nq, Ns, K, C, out);
+    } else {
+        k_max_pool_scalar<<<regtr_cdiv((long long)Nq * C, 256), 256, 0, st>>>(x, idx, Nq, Ns, K, C, out);
+    }
+    REGTR_CHECK_LAUNCH();
+    return REGTR_OK;
+}
+
+}  // extern "C"

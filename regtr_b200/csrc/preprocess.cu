@@ -1,0 +1,347 @@
+// Pyramid pre-processing kernels: voxel-grid barycentre sub-sampling, cell-list
+// construction and fixed-radius "first K in index order" neighbour search.
+//
+// Reference behaviour replaced (paths relative to /root/reference/src):
+//   models/backbone_kpconv/kpconv.py:213-240  batch_grid_subsampling_kpconv_gpu (MinkowskiEngine)
+//   models/backbone_kpconv/kpconv.py:261-288  batch_neighbors_kpconv_gpu (pytorch3d ball_query)
+// Determinism rules: DESIGN.md "H1" (shared with oracle/c/preprocess_oracle.c).
+//
+// All data-dependent sizes stay on the device: kernels are launched over host-known
+// capacities and read the real point counts from the int32 offset arrays.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned long long KEY_PAD = ~0ull;
+
+__device__ __forceinline__ int clamp_coord(int v, uint32_t* status) {
+    if (v < -32766 || v > 32766) {
+        atomicOr(status, REGTR_STATUS_KEY_RANGE);
+        v = v < 0 ? -32766 : 32766;
+    }
+    return v;
+}
+
+// key[i] = (cloud, floor(p/cell)) for i < n, KEY_PAD beyond; val[i] = i.
+__global__ void k_make_keys(const float* __restrict__ xyz, const int32_t* __restrict__ offs, int n_clouds,
+                            int n_cap, float cell, unsigned long long* __restrict__ keys,
+                            int32_t* __restrict__ vals, uint32_t* status) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cap) return;
+    const int n = offs[n_clouds];
+    unsigned long long key = KEY_PAD;
+    if (i < n) {
+        const int c = regtr_cloud_of(offs, n_clouds, i);
+        const int vx = clamp_coord(regtr_cell_of(xyz[3 * i + 0], cell), status);
+        const int vy = clamp_coord(regtr_cell_of(xyz[3 * i + 1], cell), status);
+        const int vz = clamp_coord(regtr_cell_of(xyz[3 * i + 2], cell), status);
+        key = regtr_pack_key(c, vx, vy, vz);
+    }
+    keys[i] = key;
+    vals[i] = i;
+}
+
+// flag[j] = 1 where sorted position j starts a new voxel (j < n), else 0; flag[n_cap] = 0.
+__global__ void k_head_flags(const unsigned long long* __restrict__ skeys, int n_cap, int32_t* __restrict__ flag) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > n_cap) return;
+    int f = 0;
+    if (j < n_cap) {
+        const unsigned long long k = skeys[j];
+        f = (k != KEY_PAD) && (j == 0 || skeys[j - 1] != k);
+    }
+    flag[j] = f;
+}
+
+// One thread per voxel head: fp32 running sum over the members in ascending input index
+// (the radix sort is stable, so members appear in that order), then one IEEE division.
+__global__ void k_voxel_mean(const float* __restrict__ xyz, const unsigned long long* __restrict__ skeys,
+                             const int32_t* __restrict__ sidx, const int32_t* __restrict__ rank, int n_cap,
+                             float* __restrict__ out_xyz) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cap) return;
+    const unsigned long long k = skeys[j];
+    if (k == KEY_PAD || (j > 0 && skeys[j - 1] == k)) return;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    int cnt = 0;
+    for (int t = j; t < n_cap && skeys[t] == k; ++t) {
+        const int i = sidx[t];
+        sx = __fadd_rn(sx, xyz[3 * i + 0]);
+        sy = __fadd_rn(sy, xyz[3 * i + 1]);
+        sz = __fadd_rn(sz, xyz[3 * i + 2]);
+        ++cnt;
+    }
+    const float c = (float)cnt;
+    const int m = rank[j];
+    out_xyz[3 * m + 0] = __fdiv_rn(sx, c);
+    out_xyz[3 * m + 1] = __fdiv_rn(sy, c);
+    out_xyz[3 * m + 2] = __fdiv_rn(sz, c);
+}
+
+__device__ __forceinline__ int lower_bound_u64(const unsigned long long* __restrict__ a, int lo, int hi,
+                                               unsigned long long v) {
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// out_offs[c] = number of voxels whose key is below cloud c's first key.
+__global__ void k_cloud_offsets(const unsigned long long* __restrict__ skeys, const int32_t* __restrict__ rank,
+                                int n_cap, int n_clouds, int32_t* __restrict__ out_offs) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_clouds) return;
+    if (c == n_clouds) { out_offs[c] = rank[n_cap]; return; }
+    const int pos = lower_bound_u64(skeys, 0, n_cap, (unsigned long long)c << 48);
+    out_offs[c] = rank[pos];
+}
+
+// ------------------------------------------------------------------------- cell list
+
+struct GridHeader {
+    float cell;
+    int n_cap;
+    int pad[62];
+};
+static_assert(sizeof(GridHeader) == 256, "header must stay 256 B");
+
+__global__ void k_grid_header(GridHeader* h, float cell, int n_cap) {
+    h->cell = cell;
+    h->n_cap = n_cap;
+}
+
+// sxyzi[j] = (x, y, z, bits(original index)) of the j-th point in cell order.
+__global__ void k_gather_sorted(const float* __restrict__ xyz, const unsigned long long* __restrict__ skeys,
+                                const int32_t* __restrict__ sidx, int n_cap, float4* __restrict__ sxyzi,
+                                int32_t* __restrict__ order) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cap) return;
+    const int i = sidx[j];
+    if (order) order[j] = i;
+    if (skeys[j] == KEY_PAD) { sxyzi[j] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); return; }
+    sxyzi[j] = make_float4(xyz[3 * i + 0], xyz[3 * i + 1], xyz[3 * i + 2], __int_as_float(i));
+}
+
+// ------------------------------------------------------------------------ ball query
+
+constexpr int BQ_WARPS = 8;
+constexpr int BQ_HCAP = 384;   // hit staging per warp
+constexpr int BQ_KMAX = 128;
+
+// Keep the `K` smallest of hits[0..n) in ascending order in sel[0..min(n,K)).
+__device__ __forceinline__ int select_smallest(const int* __restrict__ hits, int n, int K, int* __restrict__ sel,
+                                               int lane) {
+    for (int p = lane; p < n; p += 32) {
+        const int v = hits[p];
+        int r = 0;
+        for (int t = 0; t < n; ++t) r += (hits[t] < v);
+        if (r < K) sel[r] = v;
+    }
+    __syncwarp();
+    return n < K ? n : K;
+}
+
+__global__ void __launch_bounds__(BQ_WARPS * 32)
+k_ball_query(const float* __restrict__ q, const int32_t* __restrict__ q_offs, const int32_t* __restrict__ q_order,
+             const int32_t* __restrict__ s_offs, const GridHeader* __restrict__ hdr,
+             const unsigned long long* __restrict__ skeys, const float4* __restrict__ sxyzi, int n_clouds,
+             int nq_cap, int K, float radius, int32_t* __restrict__ out32, long long* __restrict__ out64) {
+    __shared__ int s_hits[BQ_WARPS][BQ_HCAP];
+    __shared__ int s_sel[BQ_WARPS][BQ_KMAX];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * BQ_WARPS + warp;
+    if (slot >= nq_cap) return;
+    const int nq = q_offs[n_clouds];
+    if (slot >= nq) return;
+    const int qi = q_order ? q_order[slot] : slot;
+    if (qi < 0 || qi >= nq) return;           // q_order padded entries
+    const int ns = s_offs[n_clouds];
+    const int c = regtr_cloud_of(q_offs, n_clouds, qi);
+    const float qx = q[3 * qi + 0], qy = q[3 * qi + 1], qz = q[3 * qi + 2];
+    const float cell = hdr->cell;
+    const int cx = regtr_cell_of(qx, cell), cy = regtr_cell_of(qy, cell), cz = regtr_cell_of(qz, cell);
+    const float r2 = __fmul_rn(radius, radius);
+    const int seg_lo = s_offs[c], seg_hi = s_offs[c + 1];
+
+    // lanes 0..8: one (dx,dy) column of three z-adjacent cells = one contiguous key range
+    int lo = 0, hi = 0;
+    if (lane < 9) {
+        const int x = cx + lane / 3 - 1, y = cy + lane % 3 - 1;
+        if (x >= -32767 && x <= 32767 && y >= -32767 && y <= 32767 && cz >= -32767 && cz <= 32766) {
+            const int z0 = cz - 1, z1 = cz + 1;
+            lo = lower_bound_u64(skeys, seg_lo, seg_hi, regtr_pack_key(c, x, y, z0));
+            hi = lower_bound_u64(skeys, lo, seg_hi, regtr_pack_key(c, x, y, z1) + 1ull);
+        }
+    }
+    int* hits = s_hits[warp];
+    int* sel = s_sel[warp];
+    int count = 0;
+    for (int r = 0; r < 9; ++r) {
+        const int rlo = __shfl_sync(0xffffffffu, lo, r), rhi = __shfl_sync(0xffffffffu, hi, r);
+        for (int base = rlo; base < rhi; base += 32) {
+            const int j = base + lane;
+            bool hit = false;
+            int sidx = 0;
+            if (j < rhi) {
+                const float4 sp = sxyzi[j];
+                const float dx = __fsub_rn(qx, sp.x), dy = __fsub_rn(qy, sp.y), dz = __fsub_rn(qz, sp.z);
+                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                hit = d2 < r2;
+                sidx = __float_as_int(sp.w);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (count + 32 > BQ_HCAP) {       // staging full: keep only the K smallest so far
+                __syncwarp();
+                const int kept = select_smallest(hits, count, K, sel, lane);
+                for (int t = lane; t < kept; t += 32) hits[t] = sel[t];
+                __syncwarp();
+                count = kept;
+            }
+            if (hit) hits[count + __popc(m & ((1u << lane) - 1u))] = sidx;
+            count += __popc(m);
+        }
+    }
+    __syncwarp();
+    const int kept = select_smallest(hits, count, K, sel, lane);
+    const long long row = (long long)qi * K;
+    for (int t = lane; t < K; t += 32) {
+        const int v = t < kept ? sel[t] : ns;
+        if (out32) out32[row + t] = v;
+        if (out64) out64[row + t] = v;
+    }
+}
+
+struct SubWs {
+    unsigned long long *keys_in, *keys_out;
+    int32_t *vals_in, *vals_out, *rank;
+    void* cub_tmp;
+    size_t cub_bytes;
+    size_t total;
+};
+
+size_t cub_tmp_bytes(int n_cap) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                    (int32_t*)nullptr, (int32_t*)nullptr, n_cap, 0, 64, (cudaStream_t)0);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (int32_t*)nullptr, (int32_t*)nullptr, n_cap + 1, (cudaStream_t)0);
+    return a > b ? a : b;
+}
+
+SubWs carve(void* ws, int n_cap) {
+    SubWs w;
+    char* p = (char*)ws;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += regtr_align(bytes); return (void*)r; };
+    w.keys_in = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)n_cap);
+    w.keys_out = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)n_cap);
+    w.vals_in = (int32_t*)take(sizeof(int32_t) * (size_t)n_cap);
+    w.vals_out = (int32_t*)take(sizeof(int32_t) * (size_t)n_cap);
+    w.rank = (int32_t*)take(sizeof(int32_t) * ((size_t)n_cap + 1));
+    w.cub_bytes = cub_tmp_bytes(n_cap);
+    w.cub_tmp = take(w.cub_bytes);
+    w.total = off;
+    return w;
+}
+
+int key_bits(int n_clouds) {
+    int b = 1;
+    while ((1 << b) <= n_clouds) ++b;  // 2^b > n_clouds, so the all-ones pad field sorts last
+    return 48 + b;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t regtr_grid_subsample_ws_bytes(int n_cap) { return n_cap > 0 ? carve(nullptr, n_cap).total : 256; }
+
+int regtr_grid_subsample(const float* xyz, const int32_t* offs, int n_clouds, int n_cap, float dl,
+                         float* out_xyz, int32_t* out_offs, uint32_t* status, void* ws, size_t ws_bytes,
+                         void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (!offs || !out_offs || !status || n_clouds <= 0 || n_clouds > 32767 || n_cap < 0 || !(dl > 0.f))
+        return REGTR_ERR_ARG;
+    if (n_cap == 0) {
+        cudaMemsetAsync(out_offs, 0, sizeof(int32_t) * (n_clouds + 1), st);
+        return REGTR_OK;
+    }
+    if (!xyz || !out_xyz || !ws) return REGTR_ERR_ARG;
+    SubWs w = carve(ws, n_cap);
+    if (ws_bytes < w.total) return REGTR_ERR_WORKSPACE;
+    const int T = 256;
+    k_make_keys<<<regtr_cdiv(n_cap, T), T, 0, st>>>(xyz, offs, n_clouds, n_cap, dl, w.keys_in, w.vals_in, status);
+    REGTR_CHECK_LAUNCH();
+    size_t tb = w.cub_bytes;
+    cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys_in, w.keys_out, w.vals_in, w.vals_out, n_cap, 0,
+                                    key_bits(n_clouds), st);
+    REGTR_CHECK_LAUNCH();
+    k_head_flags<<<regtr_cdiv(n_cap + 1, T), T, 0, st>>>(w.keys_out, n_cap, w.vals_in);
+    REGTR_CHECK_LAUNCH();
+    tb = w.cub_bytes;
+    cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.vals_in, w.rank, n_cap + 1, st);
+    REGTR_CHECK_LAUNCH();
+    k_voxel_mean<<<regtr_cdiv(n_cap, T), T, 0, st>>>(xyz, w.keys_out, w.vals_out, w.rank, n_cap, out_xyz);
+    REGTR_CHECK_LAUNCH();
+    k_cloud_offsets<<<regtr_cdiv(n_clouds + 1, 128), 128, 0, st>>>(w.keys_out, w.rank, n_cap, n_clouds, out_offs);
+    REGTR_CHECK_LAUNCH();
+    return REGTR_OK;
+}
+
+size_t regtr_cellgrid_bytes(int n_cap) {
+    const size_t n = n_cap > 0 ? (size_t)n_cap : 1;
+    return sizeof(GridHeader) + regtr_align(sizeof(unsigned long long) * n) + regtr_align(sizeof(float4) * n);
+}
+
+size_t regtr_cellgrid_ws_bytes(int n_cap) { return regtr_grid_subsample_ws_bytes(n_cap); }
+
+int regtr_cellgrid_build(const float* xyz, const int32_t* offs, int n_clouds, int n_cap, float cell, void* grid,
+                         int32_t* order, uint32_t* status, void* ws, size_t ws_bytes, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (!offs || !grid || !status || n_clouds <= 0 || n_clouds > 32767 || n_cap < 0 || !(cell > 0.f))
+        return REGTR_ERR_ARG;
+    GridHeader* hdr = (GridHeader*)grid;
+    k_grid_header<<<1, 1, 0, st>>>(hdr, cell, n_cap);
+    REGTR_CHECK_LAUNCH();
+    if (n_cap == 0) return REGTR_OK;
+    if (!xyz || !ws) return REGTR_ERR_ARG;
+    SubWs w = carve(ws, n_cap);
+    if (ws_bytes < w.total) return REGTR_ERR_WORKSPACE;
+    unsigned long long* skeys = (unsigned long long*)((char*)grid + sizeof(GridHeader));
+    float4* sxyzi = (float4*)((char*)skeys + regtr_align(sizeof(unsigned long long) * (size_t)n_cap));
+    const int T = 256;
+    k_make_keys<<<regtr_cdiv(n_cap, T), T, 0, st>>>(xyz, offs, n_clouds, n_cap, cell, w.keys_in, w.vals_in, status);
+    REGTR_CHECK_LAUNCH();
+    size_t tb = w.cub_bytes;
+    cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys_in, skeys, w.vals_in, w.vals_out, n_cap, 0,
+                                    key_bits(n_clouds), st);
+    REGTR_CHECK_LAUNCH();
+    k_gather_sorted<<<regtr_cdiv(n_cap, T), T, 0, st>>>(xyz, skeys, w.vals_out, n_cap, sxyzi, order);
+    REGTR_CHECK_LAUNCH();
+    return REGTR_OK;
+}
+
+int regtr_ball_query(const float* q, const int32_t* q_offs, const int32_t* q_order, const float* s,
+                     const int32_t* s_offs, const void* s_grid, int n_clouds, int nq_cap, int s_cap, int K,
+                     float radius, int32_t* out_idx32, int64_t* out_idx64, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    (void)s;  // positions are read from the cell-sorted copy inside the grid
+    if (!q_offs || !s_offs || !s_grid || n_clouds <= 0 || nq_cap < 0 || s_cap < 0 || K <= 0 || K > BQ_KMAX ||
+        !(radius > 0.f))
+        return REGTR_ERR_ARG;
+    if (nq_cap == 0) return REGTR_OK;
+    if (!q || (!out_idx32 && !out_idx64)) return REGTR_ERR_ARG;
+    const GridHeader* hdr = (const GridHeader*)s_grid;
+    const size_t n = s_cap > 0 ? (size_t)s_cap : 1;
+    const unsigned long long* skeys = (const unsigned long long*)((const char*)s_grid + sizeof(GridHeader));
+    const float4* sxyzi = (const float4*)((const char*)skeys + regtr_align(sizeof(unsigned long long) * n));
+    k_ball_query<<<regtr_cdiv(nq_cap, BQ_WARPS), BQ_WARPS * 32, 0, st>>>(
+        q, q_offs, q_order, s_offs, hdr, skeys, sxyzi, n_clouds, nq_cap, K, radius, out_idx32,
+        (long long*)out_idx64);
+    REGTR_CHECK_LAUNCH();
+    return REGTR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,320 @@
+"""KPConv backbone on the B200 kernels: pyramid pre-processor, KPConv op, blocks, encoder.
+
+Host-side mirror of the reference modules (same class names, constructor arguments,
+forward signatures and state_dict keys) for the parts of
+/root/reference/src/models/backbone_kpconv/{kpconv.py,kpconv_blocks.py} that lie on the
+RegTR hot path: `PreprocessorGPU`, `KPFEncoder`, `KPConv`,
+`BatchNormBlock` (per-cloud InstanceNorm), `UnaryBlock`, `SimpleBlock`,
+`ResnetBottleneckBlock`, `max_pool`.  Deformable / modulated KPConv, the `closest` /
+`gaussian` / `constant` modes and the decoder blocks are outside the hot path and raise
+NotImplementedError.
+
+Every numeric step runs a kernel from libregtr_b200.so (regtr_b200.ops); dense Linear
+layers go through torch (cuBLAS) as plain library GEMMs.
+"""
+from __future__ import annotations
+
+import logging
+from typing import List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .config import pyramid_plan
+from .weights import kernel_disposition
+
+_CELL_SLACK = 1.0001   # cell = radius * slack: keeps |dx| < r inside the 27-cell stencil under fp32 rounding
+
+
+# ------------------------------------------------------------------ pre-processing
+
+class PreprocessorGPU(nn.Module):
+    """Computes the KPConv pyramid metadata on the GPU, deterministically.
+
+    Same contract as the reference PreprocessorGPU.forward (kpconv.py:426-537): returns a
+    dict of per-level lists `points`, `neighbors`, `pools`, `upsamples`, `stack_lengths`
+    (int64 indices, shadow index = number of supports).  Differences by design:
+      * bit-reproducible (sorted voxel order, index-ordered fp32 sums) where the reference
+        is not (MinkowskiEngine hash order, Readme.md:99);
+      * one host synchronisation for the whole pyramid (level sizes), where the reference
+        synchronises at every `.item()` / python loop (kpconv.py:239,276-285).
+    Extra private keys (`_offs`, `_neighbors32`, `_pools32`, `_lens`) carry the int32 /
+    device-offset forms the encoder kernels consume.
+    """
+
+    def __init__(self, cfg, compute_upsamples: bool = True):
+        super().__init__()
+        self.cfg = cfg
+        self.compute_upsamples = compute_upsamples
+
+    @torch.no_grad()
+    def forward(self, pts: List[torch.Tensor]):
+        cfg = self.cfg
+        levels, _, _ = pyramid_plan(cfg)
+        device = pts[0].device
+        n_clouds = len(pts)
+        lens0 = [int(p.shape[0]) for p in pts]
+        points = torch.cat([p.to(torch.float32) for p in pts], dim=0).contiguous()
+        cap = points.shape[0]
+        status = ops.new_status(device)
+        offs_all = torch.zeros((len(levels), n_clouds + 1), dtype=torch.int32, device=device)
+        offs_all[0].copy_(ops.make_offsets(lens0, device))
+
+        pts_l, conv32, conv64, pool32, pool64, up64 = [], [], [], [], [], []
+        cur = points
+        grid = ops.CellGrid(cur, offs_all[0], n_clouds, levels[0]['radius'] * _CELL_SLACK, status)
+        for li, lvl in enumerate(levels):
+            r, K = lvl['radius'], lvl['K']
+            offs = offs_all[li]
+            pts_l.append(cur)
+            if lvl['has_conv']:
+                c32, c64 = ops.ball_query(cur, offs, cur, offs, grid, K, r, q_order=grid.order)
+            else:
+                c32 = c64 = None
+            conv32.append(c32); conv64.append(c64)
+            if lvl['strided']:
+                nxt, _ = ops.grid_subsample(cur, offs, n_clouds, lvl['dl'], status, out_offs=offs_all[li + 1])
+                p32, p64 = ops.ball_query(nxt, offs_all[li + 1], cur, offs, grid, K, r)
+                nxt_grid = ops.CellGrid(nxt, offs_all[li + 1], n_clouds, 2 * r * _CELL_SLACK, status)
+                if self.compute_upsamples:
+                    _, u64 = ops.ball_query(cur, offs, nxt, offs_all[li + 1], nxt_grid, K, 2 * r,
+                                            q_order=grid.order, want32=False)
+                else:
+                    u64 = None
+                pool32.append(p32); pool64.append(p64); up64.append(u64)
+                cur, grid = nxt, nxt_grid
+            else:
+                pool32.append(None); pool64.append(None); up64.append(None)
+
+        # ---- the single host synchronisation of the pyramid: level sizes + status word
+        host = torch.cat([offs_all.reshape(-1), status]).cpu()
+        if int(host[-1]) != 0:
+            raise RuntimeError('point coordinates exceed the +-32766-cell key range of the voxel / cell grid')
+        offs_host = host[:-1].reshape(len(levels), n_clouds + 1)
+        lens = [(offs_host[l, 1:] - offs_host[l, :-1]).tolist() for l in range(len(levels))]
+        totals = [int(offs_host[l, -1]) for l in range(len(levels))]
+
+        e_idx = torch.zeros((0, 1), dtype=torch.int64, device=device)
+        data = dict(points=[], neighbors=[], pools=[], upsamples=[], stack_lengths=[],
+                    _offs=[], _neighbors32=[], _pools32=[], _lens=lens)
+        for li, lvl in enumerate(levels):
+            n = totals[li]
+            data['points'].append(pts_l[li][:n])
+            data['neighbors'].append(conv64[li][:n] if conv64[li] is not None else e_idx)
+            data['_neighbors32'].append(conv32[li][:n] if conv32[li] is not None else None)
+            if lvl['strided']:
+                n2 = totals[li + 1]
+                data['pools'].append(pool64[li][:n2])
+                data['_pools32'].append(pool32[li][:n2])
+                data['upsamples'].append(up64[li][:n] if up64[li] is not None else e_idx)
+            else:
+                data['pools'].append(e_idx)
+                data['_pools32'].append(None)
+                data['upsamples'].append(e_idx)
+            data['stack_lengths'].append(torch.tensor(lens[li], dtype=torch.int64).to(device, non_blocking=True))
+            data['_offs'].append(offs_all[li])
+        return data
+
+
+def _meta_private(meta, device):
+    """int32 / offset forms of a pyramid dict; derived on the fly for a foreign (reference) dict."""
+    if '_offs' in meta:
+        return meta['_offs'], meta['_neighbors32'], meta['_pools32'], meta['_lens']
+    lens = [l.tolist() for l in meta['stack_lengths']]
+    offs = [ops.make_offsets(l, device) for l in lens]
+    n32 = [n.to(torch.int32).contiguous() if n.numel() and n.shape[1] > 1 else None for n in meta['neighbors']]
+    p32 = [p.to(torch.int32).contiguous() if p.numel() and p.shape[1] > 1 else None for p in meta['pools']]
+    meta.update(_offs=offs, _neighbors32=n32, _pools32=p32, _lens=lens)
+    return offs, n32, p32, lens
+
+
+# --------------------------------------------------------------------------- blocks
+
+def max_pool(x, inds):
+    """kpconv_blocks.py:127-143.  `inds` int64 (reference contract) or int32."""
+    return ops.max_pool(x.contiguous(), inds if inds.dtype == torch.int32 else inds.to(torch.int32))
+
+
+class KPConv(nn.Module):
+    """Rigid kernel-point convolution (kpconv_blocks.py:176-414), same constructor signature."""
+
+    def __init__(self, kernel_size, p_dim, in_channels, out_channels, KP_extent, radius,
+                 fixed_kernel_points='center', KP_influence='linear', aggregation_mode='sum',
+                 deformable=False, modulated=False):
+        super().__init__()
+        if deformable or modulated:
+            raise NotImplementedError('deformable / modulated KPConv is outside the hot path')
+        if KP_influence != 'linear' or aggregation_mode != 'sum':
+            raise NotImplementedError("only KP_influence='linear', aggregation_mode='sum' are on the hot path")
+        if kernel_size != 15 or p_dim != 3:
+            raise NotImplementedError('the fused kernel is specialised for 15 kernel points in 3-D')
+        self.K, self.p_dim = kernel_size, p_dim
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.radius, self.KP_extent = radius, KP_extent
+        self.weights = nn.Parameter(torch.empty((kernel_size, in_channels, out_channels), dtype=torch.float32))
+        bound = 1.0 / (in_channels * out_channels) ** 0.5      # kaiming_uniform_(a=sqrt(5)) fan-in rule
+        nn.init.uniform_(self.weights, -bound, bound)
+        # checkpoints overwrite this (the reference stores its randomised disposition in the state_dict)
+        self.kernel_points = nn.Parameter(torch.from_numpy(kernel_disposition(radius, kernel_size)),
+                                          requires_grad=False)
+
+    def forward(self, q_pts, s_pts, neighb_inds, x):
+        idx = neighb_inds if neighb_inds.dtype == torch.int32 else neighb_inds.to(torch.int32)
+        return ops.kpconv(q_pts.contiguous(), s_pts.contiguous(), idx.contiguous(), x.contiguous(),
+                          self.weights, self.kernel_points, self.KP_extent)
+
+    def __repr__(self):
+        return 'KPConv(radius: {:.2f}, extent: {:.2f}, in_feat: {:d}, out_feat: {:d})'.format(
+            self.radius, self.KP_extent, self.in_channels, self.out_channels)
+
+
+class BatchNormBlock(nn.Module):
+    """Per-cloud InstanceNorm (use_bn=True) or bias (kpconv_blocks.py:474-530).
+    `fuse(x, offs, n_clouds, res, slope)` is the fused norm(+residual)(+LeakyReLU) entry."""
+
+    def __init__(self, in_dim, use_bn, bn_momentum):
+        super().__init__()
+        self.in_dim, self.use_bn, self.bn_momentum = in_dim, use_bn, bn_momentum
+        if not use_bn:
+            self.bias = nn.Parameter(torch.zeros(in_dim, dtype=torch.float32))
+
+    def fuse(self, x, offs, n_clouds, res=None, slope=-1.0):
+        if self.use_bn:
+            return ops.instnorm_act(x, offs, n_clouds, res=res, slope=slope)
+        y = x + self.bias
+        if res is not None:
+            y = y + res
+        return F.leaky_relu(y, slope) if slope >= 0 else y
+
+    def forward(self, x, stack_lengths):
+        offs = ops.make_offsets(stack_lengths, x.device)
+        return self.fuse(x.contiguous(), offs, offs.numel() - 1)
+
+
+class UnaryBlock(nn.Module):
+    """Linear(no bias) -> InstanceNorm -> LeakyReLU(0.1) (kpconv_blocks.py:533-567)."""
+
+    def __init__(self, in_dim, out_dim, use_bn, bn_momentum, no_relu=False):
+        super().__init__()
+        self.in_dim, self.out_dim, self.use_bn, self.no_relu = in_dim, out_dim, use_bn, no_relu
+        self.mlp = nn.Linear(in_dim, out_dim, bias=False)
+        self.batch_norm = BatchNormBlock(out_dim, use_bn, bn_momentum)
+
+    def fuse(self, x, offs, n_clouds, res=None, final_slope=None):
+        slope = final_slope if final_slope is not None else (-1.0 if self.no_relu else 0.1)
+        return self.batch_norm.fuse(F.linear(x, self.mlp.weight), offs, n_clouds, res=res, slope=slope)
+
+    def forward(self, x, stack_lengths=None):
+        offs = ops.make_offsets(stack_lengths, x.device)
+        return self.fuse(x, offs, offs.numel() - 1)
+
+
+def _block_io(block, batch):
+    offs, n32, p32, _ = _meta_private(batch, batch['points'][0].device)
+    li = block.layer_ind
+    if 'strided' in block.block_name:
+        return (batch['points'][li + 1], batch['points'][li], p32[li], offs[li], offs[li + 1])
+    return (batch['points'][li], batch['points'][li], n32[li], offs[li], offs[li])
+
+
+class SimpleBlock(nn.Module):
+    """KPConv -> InstanceNorm -> LeakyReLU(0.1) (kpconv_blocks.py:590-646)."""
+
+    def __init__(self, block_name, in_dim, out_dim, radius, layer_ind, config):
+        super().__init__()
+        self.block_name, self.layer_ind = block_name, layer_ind
+        self.in_dim, self.out_dim = in_dim, out_dim
+        extent = radius * config.KP_extent / config.conv_radius
+        self.KPConv = KPConv(config.num_kernel_points, config.in_points_dim, in_dim, out_dim // 2, extent, radius,
+                             fixed_kernel_points=config.fixed_kernel_points, KP_influence=config.KP_influence,
+                             aggregation_mode=config.aggregation_mode, deformable='deform' in block_name,
+                             modulated=config.modulated)
+        self.batch_norm = BatchNormBlock(out_dim // 2, config.use_batch_norm, config.batch_norm_momentum)
+
+    def forward(self, x, batch):
+        q, s, idx, _, offs_post = _block_io(self, batch)
+        y = self.KPConv(q, s, idx, x)
+        return self.batch_norm.fuse(y, offs_post, offs_post.numel() - 1, slope=0.1)
+
+
+class ResnetBottleneckBlock(nn.Module):
+    """unary1 -> KPConv -> IN -> LReLU -> unary2(no relu) ; shortcut (max_pool if strided,
+    optional unary) ; LReLU(x + shortcut)  (kpconv_blocks.py:649-741)."""
+
+    def __init__(self, block_name, in_dim, out_dim, radius, layer_ind, config):
+        super().__init__()
+        self.block_name, self.layer_ind = block_name, layer_ind
+        self.in_dim, self.out_dim = in_dim, out_dim
+        bn, mom = config.use_batch_norm, config.batch_norm_momentum
+        extent = radius * config.KP_extent / config.conv_radius
+        mid = out_dim // 4
+        self.unary1 = UnaryBlock(in_dim, mid, bn, mom) if in_dim != mid else nn.Identity()
+        self.KPConv = KPConv(config.num_kernel_points, config.in_points_dim, mid, mid, extent, radius,
+                             fixed_kernel_points=config.fixed_kernel_points, KP_influence=config.KP_influence,
+                             aggregation_mode=config.aggregation_mode, deformable='deform' in block_name,
+                             modulated=config.modulated)
+        self.batch_norm_conv = BatchNormBlock(mid, bn, mom)
+        self.unary2 = UnaryBlock(mid, out_dim, bn, mom, no_relu=True)
+        self.unary_shortcut = UnaryBlock(in_dim, out_dim, bn, mom, no_relu=True) if in_dim != out_dim \
+            else nn.Identity()
+
+    def forward(self, features, batch):
+        q, s, idx, offs_pre, offs_post = _block_io(self, batch)
+        nc = offs_pre.numel() - 1
+        x = self.unary1.fuse(features, offs_pre, nc) if isinstance(self.unary1, UnaryBlock) else features
+        x = self.KPConv(q, s, idx, x)
+        x = self.batch_norm_conv.fuse(x, offs_post, nc, slope=0.1)
+        shortcut = ops.max_pool(features, idx) if 'strided' in self.block_name else features
+        if isinstance(self.unary_shortcut, UnaryBlock):
+            shortcut = self.unary_shortcut.fuse(shortcut, offs_post, nc)
+        # LeakyReLU(unary2(x) + shortcut), fused into unary2's normalisation pass
+        return self.unary2.fuse(x, offs_post, nc, res=shortcut, final_slope=0.1)
+
+
+def block_decider(block_name, radius, in_dim, out_dim, layer_ind, config):
+    """kpconv_blocks.py:429-471, restricted to the block kinds either config selects."""
+    if block_name in ('simple', 'simple_strided'):
+        return SimpleBlock(block_name, in_dim, out_dim, radius, layer_ind, config)
+    if block_name in ('resnetb', 'resnetb_strided'):
+        return ResnetBottleneckBlock(block_name, in_dim, out_dim, radius, layer_ind, config)
+    raise NotImplementedError(f'block {block_name!r} is outside the RegTR hot path (SURVEY.md 2 row 3)')
+
+
+class KPFEncoder(nn.Module):
+    """KPConv encoder (kpconv.py:22-88): same constructor, `encoder_blocks`, `encoder_skip_dims`."""
+
+    def __init__(self, config, d_bottle, increase_channel_when_downsample=True):
+        super().__init__()
+        self.logger = logging.getLogger(__name__)
+        octave = 0
+        r = config.first_subsampling_dl * config.conv_radius
+        in_dim, out_dim = config.in_feats_dim, config.first_feats_dim
+        self.encoder_blocks = nn.ModuleList()
+        self.encoder_skip_dims, self.encoder_skips = [], []
+        block = None
+        for block_i, block in enumerate(config.architecture):
+            if any(t in block for t in ('pool', 'strided', 'upsample', 'global')):
+                self.encoder_skips.append(block_i)
+                self.encoder_skip_dims.append(in_dim)
+            if 'upsample' in block:
+                break
+            self.encoder_blocks.append(block_decider(block, r, in_dim, out_dim, octave, config))
+            in_dim = out_dim // 2 if 'simple' in block else out_dim
+            if 'pool' in block or 'strided' in block:
+                octave += 1
+                r *= 2
+                if increase_channel_when_downsample:
+                    out_dim *= 2
+        if 'upsample' not in block:
+            self.encoder_skips.append(block_i)
+            self.encoder_skip_dims.append(in_dim)
+
+    def forward(self, x, batch):
+        skip_x = []
+        for block_i, block_op in enumerate(self.encoder_blocks):
+            if block_i in self.encoder_skips:
+                skip_x.append(x)
+            x = block_op(x, batch)
+        return x, skip_x

@@ -1,0 +1,281 @@
+"""Torch-tensor front end of the C ABI (one function per entry point of include/regtr_b200.h).
+
+PyTorch is used for device memory and streams only; every operation below runs a
+hand-written sm_100a kernel from libregtr_b200.so on the current CUDA stream.
+Tensors must live on a CUDA device; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import lib as _lib
+
+_ws_cache = {}
+
+# Number of hand-written kernels (libregtr_b200.so, excluding CUB / cuBLAS) launched so far.
+LAUNCHES = 0
+# Optional profiler: when set to a list, ops.kpconv appends (cuda start event, end event, info dict)
+# around every KPConv call so that bench.py can time the dominant kernel on its own stream.
+KPCONV_TRACE = None
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name, dims=None):
+    if not t.is_cuda:
+        raise _lib.RegtrLibError(f'{name}: expected a CUDA tensor (the product path has no CPU fallback)')
+    if t.dtype != dtype:
+        raise TypeError(f'{name}: expected {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise ValueError(f'{name}: must be contiguous')
+    if dims is not None and t.dim() != dims:
+        raise ValueError(f'{name}: expected {dims}-d tensor, got shape {tuple(t.shape)}')
+    return t
+
+
+def workspace(nbytes: int, device, slot: str = 'default') -> torch.Tensor:
+    """Per-(device, slot) grow-only scratch buffer (stream-ordered reuse)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def make_offsets(lengths, device) -> torch.Tensor:
+    """int32 prefix offsets (n_clouds+1) on `device` from a host list / tensor of lengths."""
+    if torch.is_tensor(lengths):
+        lengths = lengths.tolist()
+    offs = [0]
+    for v in lengths:
+        offs.append(offs[-1] + int(v))
+    return torch.tensor(offs, dtype=torch.int32, device=device)
+
+
+def new_status(device) -> torch.Tensor:
+    return torch.zeros(1, dtype=torch.int32, device=device)
+
+
+# ---------------------------------------------------------------- pre-processing
+
+def grid_subsample(xyz, offs, n_clouds: int, dl: float, status, out_xyz=None, out_offs=None):
+    """-> (out_xyz (n_cap,3) capacity buffer, out_offs (n_clouds+1) int32).  No host sync."""
+    L = _lib.load()
+    _chk(xyz, torch.float32, 'xyz', 2); _chk(offs, torch.int32, 'offs', 1)
+    n_cap = xyz.shape[0]
+    out_xyz = torch.empty_like(xyz) if out_xyz is None else out_xyz
+    out_offs = torch.empty(n_clouds + 1, dtype=torch.int32, device=xyz.device) if out_offs is None else out_offs
+    nb = L.regtr_grid_subsample_ws_bytes(n_cap)
+    ws = workspace(nb, xyz.device)
+    _lib.check(L.regtr_grid_subsample(_p(xyz), _p(offs), n_clouds, n_cap, float(dl), _p(out_xyz), _p(out_offs),
+                                      _p(status), _p(ws), ws.numel(), _stream()), 'regtr_grid_subsample')
+    _count(4)
+    return out_xyz, out_offs
+
+
+class CellGrid:
+    """Opaque cell list over a stacked point set (+ the cell-sorted point order)."""
+
+    def __init__(self, xyz, offs, n_clouds: int, cell: float, status):
+        L = _lib.load()
+        _chk(xyz, torch.float32, 'xyz', 2); _chk(offs, torch.int32, 'offs', 1)
+        self.n_cap = xyz.shape[0]
+        self.n_clouds = n_clouds
+        self.cell = float(cell)
+        self.buf = torch.empty(L.regtr_cellgrid_bytes(self.n_cap), dtype=torch.uint8, device=xyz.device)
+        self.order = torch.empty(max(self.n_cap, 1), dtype=torch.int32, device=xyz.device)
+        ws = workspace(L.regtr_cellgrid_ws_bytes(self.n_cap), xyz.device)
+        _lib.check(L.regtr_cellgrid_build(_p(xyz), _p(offs), n_clouds, self.n_cap, self.cell, _p(self.buf),
+                                          _p(self.order), _p(status), _p(ws), ws.numel(), _stream()),
+                   'regtr_cellgrid_build')
+        _count(3)
+
+
+def ball_query(q, q_offs, s, s_offs, grid: CellGrid, K: int, radius: float, q_order=None,
+               want32=True, want64=True):
+    """First-K-in-index-order radius search.  -> (idx32 or None, idx64 or None), shape (nq_cap,K)."""
+    L = _lib.load()
+    _chk(q, torch.float32, 'q', 2); _chk(s, torch.float32, 's', 2)
+    nq_cap = q.shape[0]
+    if grid.n_cap != s.shape[0]:
+        raise ValueError('grid was built over a different support capacity')
+    if grid.cell < float(radius):
+        raise ValueError('grid cell must be >= radius')
+    i32 = torch.empty((nq_cap, K), dtype=torch.int32, device=q.device) if want32 else None
+    i64 = torch.empty((nq_cap, K), dtype=torch.int64, device=q.device) if want64 else None
+    _lib.check(L.regtr_ball_query(_p(q), _p(q_offs), _p(q_order), _p(s), _p(s_offs), _p(grid.buf), grid.n_clouds,
+                                  nq_cap, s.shape[0], int(K), float(radius), _p(i32), _p(i64), _stream()),
+               'regtr_ball_query')
+    _count(1)
+    return i32, i64
+
+
+# ------------------------------------------------------------------------ encoder
+
+def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=None):
+    """KPConv.forward (rigid / linear / sum).  idx32 (Nq,K) int32, x (Ns,Cin) -> (Nq,Cout)."""
+    L = _lib.load()
+    _chk(q_pts, torch.float32, 'q_pts', 2); _chk(s_pts, torch.float32, 's_pts', 2)
+    _chk(idx32, torch.int32, 'neighb_inds', 2); _chk(x, torch.float32, 'x', 2)
+    _chk(weights, torch.float32, 'weights', 3); _chk(kernel_points, torch.float32, 'kernel_points', 2)
+    Nq, K = idx32.shape
+    Ns, Cin = x.shape
+    P, Cin_w, Cout = weights.shape
+    if P != 15 or kernel_points.shape != (15, 3) or Cin_w != Cin or q_pts.shape[0] != Nq or s_pts.shape[0] != Ns:
+        raise ValueError('kpconv: inconsistent shapes')
+    out = torch.empty((Nq, Cout), dtype=torch.float32, device=x.device) if out is None else out
+    nb = L.regtr_kpconv_ws_bytes(Nq, Ns, Cin)
+    ws = workspace(nb, x.device, 'kpconv')
+    trace = KPCONV_TRACE
+    if trace is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.check(L.regtr_kpconv_fwd(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(weights), _p(kernel_points), Nq, Ns, K,
+                                  Cin, Cout, float(extent), _p(out), _p(ws), ws.numel(), _stream()),
+               'regtr_kpconv_fwd')
+    if trace is not None:
+        e1.record()
+        trace.append((e0, e1, dict(Nq=Nq, Ns=Ns, K=K, Cin=Cin, Cout=Cout, idx=idx32)))
+    _count(2)
+    return out
+
+
+def kpconv_aggregate(q_pts, s_pts, idx32, x, kernel_points, extent: float, wf=None):
+    """Gather + influence + aggregation only: -> wf (Nq, 15*Cin) (already / neighbour count)."""
+    L = _lib.load()
+    Nq, K = idx32.shape
+    Ns, Cin = x.shape
+    wf = torch.empty((Nq, 15 * Cin), dtype=torch.float32, device=x.device) if wf is None else wf
+    flags = workspace(max(Ns, 1), x.device, 'rowflags')
+    _lib.check(L.regtr_kpconv_aggregate(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(kernel_points), Nq, Ns, K, Cin,
+                                        float(extent), _p(wf), _p(flags), _stream()), 'regtr_kpconv_aggregate')
+    _count(2)
+    return wf
+
+
+def max_pool(x, idx32):
+    L = _lib.load()
+    _chk(x, torch.float32, 'x', 2); _chk(idx32, torch.int32, 'inds', 2)
+    Nq, K = idx32.shape
+    out = torch.empty((Nq, x.shape[1]), dtype=torch.float32, device=x.device)
+    _lib.check(L.regtr_max_pool(_p(x), _p(idx32), Nq, x.shape[0], K, x.shape[1], _p(out), _stream()),
+               'regtr_max_pool')
+    _count(1)
+    return out
+
+
+def instnorm_act(x, offs, n_clouds: int, res=None, slope: float = -1.0, eps: float = 1e-5, out=None):
+    """out = act(InstanceNorm_per_cloud(x) + res); slope < 0 -> no activation."""
+    L = _lib.load()
+    _chk(x, torch.float32, 'x', 2); _chk(offs, torch.int32, 'offs', 1)
+    n, C = x.shape
+    if res is not None:
+        _chk(res, torch.float32, 'res', 2)
+    out = torch.empty_like(x) if out is None else out
+    nb = L.regtr_instnorm_ws_bytes(n, n_clouds, C)
+    ws = workspace(nb, x.device, 'instnorm')
+    _lib.check(L.regtr_instnorm_act(_p(x), _p(offs), n_clouds, n, C, float(eps), _p(res), float(slope), _p(out),
+                                    _p(ws), ws.numel(), _stream()), 'regtr_instnorm_act')
+    _count(2)
+    return out
+
+
+# -------------------------------------------------------------------- transformer
+
+_dim_t_cache = {}
+
+
+def sine_dim_t(n_freq: int, temperature: float, device):
+    """The reference's frequency table, computed with the same torch fp32 ops
+    (position_embedding.py:39-40) and cached per device."""
+    key = (n_freq, float(temperature), str(device))
+    if key not in _dim_t_cache:
+        d = torch.arange(n_freq, dtype=torch.float32)
+        d = temperature ** (2 * torch.div(d, 2, rounding_mode='trunc') / n_freq)
+        _dim_t_cache[key] = d.to(device)
+    return _dim_t_cache[key]
+
+
+def pos_embed_sine(xyz, d_model: int = 256, temperature: float = 10000.0, scale: float = 1.0):
+    L = _lib.load()
+    _chk(xyz, torch.float32, 'xyz', 2)
+    n, n_dim = xyz.shape
+    if n_dim != 3:
+        raise ValueError('pos_embed_sine: only 3-D coordinates are on the hot path')
+    n_freq = d_model // n_dim // 2 * 2
+    out = torch.empty((n, d_model), dtype=torch.float32, device=xyz.device)
+    s32 = torch.tensor(scale * 2 * math.pi, dtype=torch.float32).item()
+    _lib.check(L.regtr_pos_embed_sine(_p(xyz), n, _p(sine_dim_t(n_freq, temperature, xyz.device)), n_freq, d_model,
+                                      s32, _p(out), _stream()), 'regtr_pos_embed_sine')
+    _count(1)
+    return out
+
+
+def layernorm_pos(x, gamma, beta, pos=None, eps: float = 1e-5, want_plain=True, want_pos=True):
+    """-> (LN(x), LN(x)+pos); either may be skipped."""
+    L = _lib.load()
+    _chk(x, torch.float32, 'x', 2)
+    n, E = x.shape
+    y = torch.empty_like(x) if want_plain else None
+    yp = torch.empty_like(x) if want_pos else None
+    _lib.check(L.regtr_layernorm_pos(_p(x), _p(gamma), _p(beta), _p(pos), n, E, float(eps), _p(y), _p(yp), _stream()),
+               'regtr_layernorm_pos')
+    _count(1)
+    return y, yp
+
+
+def mha_varlen(q, k, v, q_start, q_len, k_start, k_len, max_q_len: int, n_heads: int, out=None):
+    """softmax(q k^T / sqrt(dh)) v per head over explicit (query range, key range) problems.
+    q/k/v may be column slices of a wider row-major matrix (stride(0) is the leading dim)."""
+    L = _lib.load()
+    for t, nm in ((q, 'q'), (k, 'k'), (v, 'v')):
+        if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+            raise ValueError(f'mha_varlen: {nm} must be a CUDA fp32 matrix with unit column stride')
+    E = q.shape[1]
+    dh = E // n_heads
+    out = torch.empty((q.shape[0], E), dtype=torch.float32, device=q.device) if out is None else out
+    _lib.check(L.regtr_mha_varlen_fwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
+                                      out.stride(0), _p(q_start), _p(q_len), _p(k_start), _p(k_len),
+                                      q_start.numel(), int(max_q_len), n_heads, dh, 1.0 / math.sqrt(dh), _stream()),
+               'regtr_mha_varlen_fwd')
+    _count(1)
+    return out
+
+
+# --------------------------------------------------------------------------- pose
+
+def kabsch(a, b, w, offs):
+    """Packed problems: rows [offs[i], offs[i+1]) -> T (n_problems,3,4)."""
+    L = _lib.load()
+    _chk(a, torch.float32, 'a', 2); _chk(b, torch.float32, 'b', 2); _chk(w, torch.float32, 'w', 1)
+    n_prob = offs.numel() - 1
+    T = torch.empty((n_prob, 3, 4), dtype=torch.float32, device=a.device)
+    _lib.check(L.regtr_kabsch_fwd(_p(a), _p(b), _p(w), _p(offs), n_prob, _p(T), _stream()), 'regtr_kabsch_fwd')
+    _count(1)
+    return T
+
+
+def pose_from_corr(kp, corr, logit, offs, B: int):
+    """kp (n,3), corr (L,n,3), logit (L,n), offs (2B+1) -> pose (L,B,3,4)."""
+    L_ = _lib.load()
+    _chk(kp, torch.float32, 'kp', 2); _chk(corr, torch.float32, 'corr', 3); _chk(logit, torch.float32, 'logit', 2)
+    nl, n = logit.shape
+    pose = torch.empty((nl, B, 3, 4), dtype=torch.float32, device=kp.device)
+    _lib.check(L_.regtr_pose_from_corr(_p(kp), _p(corr), _p(logit), _p(offs), n, B, nl, _p(pose), _stream()),
+               'regtr_pose_from_corr')
+    _count(1)
+    return pose

@@ -1,0 +1,187 @@
+"""Stacked self/cross attention over the down-sampled point features, on the B200 kernels.
+
+Host-side mirror of /root/reference/src/models/transformer/{transformers.py,
+position_embedding.py} for the branches both configs select: pre-norm
+`TransformerCrossEncoderLayer.forward_pre` (transformers.py:183-244), `TransformerCrossEncoder`
+with `return_intermediate` + final norm (18-59) and `PositionEmbeddingCoordsSine` (7-50).
+Same constructor signatures and state_dict keys (`self_attn.in_proj_weight`, ...).
+
+Design: the reference pads every cloud to the longest one ((L,B,D) tensors + key-padding
+masks).  Here tokens stay PACKED in one (N,D) matrix -- src clouds first, then tgt clouds,
+the order the KPConv encoder already produces -- and attention runs over explicit
+(query range, key range) problems, so no FLOP or byte is spent on padding.  The padded
+reference-style `forward` is kept as a thin adaptor around `forward_packed`.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+
+from . import ops
+
+
+class PositionEmbeddingCoordsSine(nn.Module):
+    """position_embedding.py:7-50 (same constructor)."""
+
+    def __init__(self, n_dim: int = 1, d_model: int = 256, temperature=10000, scale=None):
+        super().__init__()
+        self.n_dim, self.d_model, self.temperature = n_dim, d_model, temperature
+        self.num_pos_feats = d_model // n_dim // 2 * 2
+        self.padding = d_model - self.num_pos_feats * n_dim
+        self.scale_arg = 1.0 if scale is None else scale
+
+    def forward(self, xyz: Tensor) -> Tensor:
+        lead = xyz.shape[:-1]
+        out = ops.pos_embed_sine(xyz.reshape(-1, self.n_dim).contiguous(), self.d_model, self.temperature,
+                                 self.scale_arg)
+        return out.reshape(*lead, self.d_model)
+
+
+class _MHAParams(nn.Module):
+    """Parameter container with nn.MultiheadAttention's state_dict layout."""
+
+    def __init__(self, d_model, nhead):
+        super().__init__()
+        self.embed_dim, self.num_heads = d_model, nhead
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * d_model, d_model))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * d_model))
+        self.out_proj = nn.Linear(d_model, d_model)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.zeros_(self.out_proj.bias)
+
+
+class AttentionPlan:
+    """Device-side (start,len) tables of the self and cross attention problems of a batch."""
+
+    def __init__(self, lens, device):
+        n2 = len(lens)
+        B = n2 // 2
+        starts = [0]
+        for v in lens:
+            starts.append(starts[-1] + int(v))
+        other = [B + c if c < B else c - B for c in range(n2)]
+        rows = [starts[:n2], list(map(int, lens)),                      # query ranges (self and cross)
+                [starts[o] for o in other], [int(lens[o]) for o in other]]  # cross key ranges
+        t = torch.tensor(rows, dtype=torch.int32).to(device)
+        self.q_start, self.q_len, self.xk_start, self.xk_len = t[0], t[1], t[2], t[3]
+        self.max_len = max(map(int, lens)) if n2 else 0
+        self.n_tokens = starts[-1]
+
+
+class TransformerCrossEncoderLayer(nn.Module):
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu",
+                 normalize_before=False, sa_val_has_pos_emb=False, ca_val_has_pos_emb=False,
+                 attention_type='dot_prod'):
+        super().__init__()
+        if attention_type != 'dot_prod':
+            raise NotImplementedError
+        if not normalize_before:
+            raise NotImplementedError('forward_post is outside the hot path (both configs use pre_norm)')
+        if activation != 'relu':
+            raise NotImplementedError('only relu is on the hot path')
+        if dropout != 0.0:
+            raise NotImplementedError('dropout > 0 is a training-only branch')
+        self.self_attn = _MHAParams(d_model, nhead)
+        self.multihead_attn = _MHAParams(d_model, nhead)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.norm3 = nn.LayerNorm(d_model)
+        self.nhead = nhead
+        self.normalize_before = normalize_before
+        self.sa_val_has_pos_emb, self.ca_val_has_pos_emb = sa_val_has_pos_emb, ca_val_has_pos_emb
+        self.satt_weights, self.xatt_weights = None, None   # analysis only (reference: get_attentions)
+
+    def _attend(self, mha: _MHAParams, x2, x2p, val_has_pos, plan: AttentionPlan, cross: bool):
+        E = mha.embed_dim
+        W, b = mha.in_proj_weight, mha.in_proj_bias
+        if val_has_pos:
+            qkv = F.linear(x2p, W, b)                     # one packed in-projection GEMM
+            q, k, v = qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:]
+        else:
+            qk = F.linear(x2p, W[:2 * E], b[:2 * E])
+            q, k = qk[:, :E], qk[:, E:]
+            v = F.linear(x2, W[2 * E:], b[2 * E:])
+        ks, kl = (plan.xk_start, plan.xk_len) if cross else (plan.q_start, plan.q_len)
+        o = ops.mha_varlen(q, k, v, plan.q_start, plan.q_len, ks, kl, plan.max_len, self.nhead)
+        return o
+
+    def forward_packed(self, x, pos, plan: AttentionPlan):
+        """x, pos: (N,E) packed tokens (src clouds then tgt clouds).  Returns updated x."""
+        has_pos = pos is not None
+        # self attention (shared weights for src and tgt: one launch over all 2B clouds)
+        x2, x2p = ops.layernorm_pos(x, self.norm1.weight, self.norm1.bias, pos, self.norm1.eps,
+                                    want_plain=not self.sa_val_has_pos_emb, want_pos=True)
+        o = self._attend(self.self_attn, x2, x2p, self.sa_val_has_pos_emb or not has_pos, plan, cross=False)
+        x = torch.addmm(x, o, self.self_attn.out_proj.weight.t()).add_(self.self_attn.out_proj.bias)
+        # cross attention, both directions from the same pre-update normalised features
+        x2, x2p = ops.layernorm_pos(x, self.norm2.weight, self.norm2.bias, pos, self.norm2.eps,
+                                    want_plain=not self.ca_val_has_pos_emb, want_pos=True)
+        o = self._attend(self.multihead_attn, x2, x2p, self.ca_val_has_pos_emb or not has_pos, plan, cross=True)
+        x = torch.addmm(x, o, self.multihead_attn.out_proj.weight.t()).add_(self.multihead_attn.out_proj.bias)
+        # position-wise feed-forward
+        x2, _ = ops.layernorm_pos(x, self.norm3.weight, self.norm3.bias, None, self.norm3.eps,
+                                  want_plain=True, want_pos=False)
+        h = F.relu_(F.linear(x2, self.linear1.weight, self.linear1.bias))
+        x = torch.addmm(x, h, self.linear2.weight.t()).add_(self.linear2.bias)
+        return x
+
+
+def _get_clones(module, N):
+    return nn.ModuleList([copy.deepcopy(module) for _ in range(N)])
+
+
+class TransformerCrossEncoder(nn.Module):
+    def __init__(self, cross_encoder_layer, num_layers, norm=None, return_intermediate=False):
+        super().__init__()
+        self.layers = _get_clones(cross_encoder_layer, num_layers)
+        self.num_layers = num_layers
+        self.norm = norm
+        self.return_intermediate = return_intermediate
+
+    def forward_packed(self, x, pos, plan: AttentionPlan):
+        """-> (n_out, N, E): final-normed output of every layer (return_intermediate) or the last."""
+        outs = []
+        for layer in self.layers:
+            x = layer.forward_packed(x, pos, plan)
+            if self.return_intermediate:
+                outs.append(self._final(x))
+        if not self.return_intermediate:
+            outs.append(self._final(x))
+        return torch.stack(outs)
+
+    def _final(self, x):
+        if self.norm is None:
+            return x
+        y, _ = ops.layernorm_pos(x, self.norm.weight, self.norm.bias, None, self.norm.eps, True, False)
+        return y
+
+    def forward(self, src, tgt, src_mask: Optional[Tensor] = None, tgt_mask: Optional[Tensor] = None,
+                src_key_padding_mask: Optional[Tensor] = None, tgt_key_padding_mask: Optional[Tensor] = None,
+                src_pos: Optional[Tensor] = None, tgt_pos: Optional[Tensor] = None):
+        """Reference-compatible padded interface (transformers.py:27-59): (L,B,D) in, (n_out,L,B,D) out.
+        Padded rows of the outputs are zero (the reference leaves unspecified values there)."""
+        assert src_mask is None and tgt_mask is None, 'Masking not implemented'
+        B = src.shape[1]
+        s_lens = (~src_key_padding_mask).sum(1).tolist() if src_key_padding_mask is not None else [src.shape[0]] * B
+        t_lens = (~tgt_key_padding_mask).sum(1).tolist() if tgt_key_padding_mask is not None else [tgt.shape[0]] * B
+
+        def pack(padded, lens):
+            return [padded[:l, b] for b, l in enumerate(lens)]
+        x = torch.cat(pack(src, s_lens) + pack(tgt, t_lens), 0).contiguous()
+        pos = None
+        if src_pos is not None:
+            pos = torch.cat(pack(src_pos, s_lens) + pack(tgt_pos, t_lens), 0).contiguous()
+        plan = AttentionPlan(s_lens + t_lens, x.device)
+        out = self.forward_packed(x, pos, plan)
+        parts = torch.split(out, s_lens + t_lens, dim=1)
+        pad = torch.nn.utils.rnn.pad_sequence
+        src_out = pad([p.transpose(0, 1) for p in parts[:B]]).permute(2, 0, 1, 3)
+        tgt_out = pad([p.transpose(0, 1) for p in parts[B:]]).permute(2, 0, 1, 3)
+        return src_out, tgt_out

@@ -1,0 +1,262 @@
+"""GPU parity tests (run on the B200 box): the CUDA product, called through the C ABI, against
+(a) the golden fixtures produced by the unmodified reference and (b) the CPU oracle on the same
+seeded inputs.  Integer / index results must be bit-exact; float tolerances are stated per test
+(features <= 1e-4 * max|ref|, correspondences <= 1e-5 m ... pose <= 1e-4)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import FORWARD_CASES, check_forward_against_golden, load_golden, make_case
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda:0'
+
+
+def G(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(DEV) if dtype is None else t.to(DEV, dtype)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _native_loaded():
+    from regtr_b200 import lib
+    lib.load()
+    assert torch.cuda.is_available()
+
+
+# ------------------------------------------------------------------ op-level goldens
+
+def test_kpconv_vs_reference_golden(ops_golden):
+    from regtr_b200 import ops
+    g = ops_golden
+    y = ops.kpconv(G(g['kp_q']), G(g['kp_s']), G(g['kp_inds'], torch.int32), G(g['kp_x']), G(g['kp_W']),
+                   G(g['kp_kp']), float(g['kp_extent']))
+    assert np.abs(N(y) - g['kp_out']).max() <= 2e-5 * np.abs(g['kp_out']).max()
+    assert np.all(N(y)[3] == 0)
+
+
+@pytest.mark.parametrize('cin,cout', [(1, 64), (32, 32), (64, 64), (128, 128), (256, 256)])
+def test_kpconv_all_channel_paths_vs_oracle(cin, cout):
+    from oracle import regtr_oracle as O
+    from regtr_b200 import ops
+    rng = np.random.default_rng(cin)
+    Nq, Ns, K = 301, 457, 40
+    q = rng.normal(size=(Nq, 3)).astype(np.float32) * 0.05
+    s = rng.normal(size=(Ns, 3)).astype(np.float32) * 0.05
+    idx = rng.integers(0, Ns + 1, size=(Nq, K))
+    idx[:, 30:] = np.where(rng.random((Nq, 10)) < 0.7, Ns, idx[:, 30:])     # shadow tails
+    idx[7] = Ns
+    x = rng.normal(size=(Ns, cin)).astype(np.float32) + (1.0 if cin == 1 else 0.0)
+    W = (rng.normal(size=(15, cin, cout)) / np.sqrt(15 * cin)).astype(np.float32)
+    kp = (rng.normal(size=(15, 3)) * 0.03).astype(np.float32)
+    want = O.kpconv(*(torch.from_numpy(a) for a in (q, s)), torch.from_numpy(idx), torch.from_numpy(x),
+                    torch.from_numpy(W), torch.from_numpy(kp), 0.05).numpy()
+    got = N(ops.kpconv(G(q), G(s), G(idx, torch.int32), G(x), G(W), G(kp), 0.05))
+    assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+
+
+def test_maxpool_instnorm_posemb_vs_reference_golden(ops_golden):
+    from regtr_b200 import ops
+    g = ops_golden
+    assert np.array_equal(N(ops.max_pool(G(g['kp_x']), G(g['kp_inds'], torch.int32))), g['maxpool_out'])
+    offs = ops.make_offsets(g['inorm_lens'].tolist(), DEV)
+    np.testing.assert_allclose(N(ops.instnorm_act(G(g['kp_x']), offs, 2)), g['inorm_out'], rtol=0, atol=3e-6)
+    np.testing.assert_allclose(N(ops.pos_embed_sine(G(g['pe_xyz']))), g['pe_out'], rtol=0, atol=2e-6)
+
+
+def test_instnorm_residual_act_large():
+    from oracle import regtr_oracle as O
+    from regtr_b200 import ops
+    rng = np.random.default_rng(3)
+    lens = [2500, 1, 3000, 777]
+    x = (rng.normal(size=(sum(lens), 96)) * 3 + 5).astype(np.float32)
+    res = rng.normal(size=x.shape).astype(np.float32)
+    want = torch.nn.functional.leaky_relu(O.instance_norm(torch.from_numpy(x), lens) + torch.from_numpy(res), 0.1)
+    got = ops.instnorm_act(G(x), ops.make_offsets(lens, DEV), 4, res=G(res), slope=0.1)
+    np.testing.assert_allclose(N(got), want.numpy(), rtol=0, atol=5e-6)
+
+
+def test_kabsch_vs_reference_golden(ops_golden):
+    from regtr_b200.se3 import compute_rigid_transform
+    g = ops_golden
+    T = N(compute_rigid_transform(G(g['kabsch_a']), G(g['kabsch_b']), G(g['kabsch_w'])))
+    np.testing.assert_allclose(T, g['kabsch_T'], rtol=0, atol=2e-5)
+    assert np.all(np.linalg.det(T[..., :3].astype(np.float64)) > 0.999)
+
+
+def test_kabsch_well_conditioned_vs_fp64():
+    """Kabsch kernel alone <= 1e-6 vs an fp64 solve on well-conditioned correspondences."""
+    from oracle import regtr_oracle as O
+    from regtr_b200.se3 import compute_rigid_transform
+    rng = np.random.default_rng(11)
+    a = rng.normal(size=(24, 900, 3))
+    R = np.stack([np.linalg.qr(rng.normal(size=(3, 3)))[0] for _ in range(24)])
+    R *= np.sign(np.linalg.det(R))[:, None, None]
+    b = np.einsum('bij,bnj->bni', R, a) + rng.normal(size=(24, 1, 3)) + rng.normal(size=a.shape) * 0.01
+    w = rng.uniform(0, 1, size=(24, 900))
+    want = O.kabsch(torch.from_numpy(a), torch.from_numpy(b), torch.from_numpy(w)).numpy()
+    got = N(compute_rigid_transform(G(a, torch.float32), G(b, torch.float32), G(w, torch.float32)))
+    assert np.abs(got - want).max() <= 1e-6
+
+
+def test_cross_encoder_padded_api_vs_reference_golden(ops_golden):
+    """Reference-style padded interface of TransformerCrossEncoder, B=2, vs the reference's outputs."""
+    from regtr_b200.config import get_config
+    from regtr_b200.transformer import (PositionEmbeddingCoordsSine, TransformerCrossEncoder,
+                                        TransformerCrossEncoderLayer)
+    from regtr_b200.weights import random_state_dict
+    g = ops_golden
+    cfg = get_config('3dmatch')
+    sd = random_state_dict(cfg, 21)
+    layer = TransformerCrossEncoderLayer(256, 8, 1024, 0.0, activation='relu', normalize_before=True,
+                                         sa_val_has_pos_emb=True, ca_val_has_pos_emb=True)
+    enc = TransformerCrossEncoder(layer, 6, torch.nn.LayerNorm(256), return_intermediate=True)
+    enc.load_state_dict({k[len('transformer_encoder.'):]: v for k, v in sd.items()
+                         if k.startswith('transformer_encoder.')}, strict=True)
+    enc = enc.to(DEV).eval()
+    pe = PositionEmbeddingCoordsSine(3, 256, scale=1.0)
+    pad = torch.nn.utils.rnn.pad_sequence
+    src = [G(g[f'xenc_src_{b}']) for b in range(2)]
+    tgt = [G(g[f'xenc_tgt_{b}']) for b in range(2)]
+    spe = [pe(G(g[f'xenc_sxyz_{b}'])) for b in range(2)]
+    tpe = [pe(G(g[f'xenc_txyz_{b}'])) for b in range(2)]
+
+    def mask(ts):
+        m = torch.zeros((len(ts), max(t.shape[0] for t in ts)), dtype=torch.bool, device=DEV)
+        for i, t in enumerate(ts):
+            m[i, t.shape[0]:] = True
+        return m
+    with torch.no_grad():
+        so, to = enc(pad(src), pad(tgt), src_key_padding_mask=mask(src), tgt_key_padding_mask=mask(tgt),
+                     src_pos=pad(spe), tgt_pos=pad(tpe))
+    for b in range(2):
+        np.testing.assert_allclose(N(so[:, :src[b].shape[0], b]), g[f'xenc_src_out_{b}'], rtol=0, atol=5e-5)
+        np.testing.assert_allclose(N(to[:, :tgt[b].shape[0], b]), g[f'xenc_tgt_out_{b}'], rtol=0, atol=5e-5)
+
+
+# ------------------------------------------------------------- pre-processing, bit-exact
+
+def _pre_inputs(seed, lens, scale=0.5, snap=0.05):
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(-scale, scale, size=(sum(lens), 3)).astype(np.float32)
+    k = min(64, len(pts))
+    pts[:k] = np.round(pts[:k] / snap) * snap          # points exactly on voxel / cell faces
+    return pts
+
+
+@pytest.mark.parametrize('lens', [[900, 1100], [1, 2000, 0, 37], [5000]])
+def test_grid_subsample_and_ball_query_bit_exact(lens):
+    from oracle import pre
+    from regtr_b200 import ops
+    pts = _pre_inputs(sum(lens), lens)
+    dl, r, K = 0.05, 0.0625, 40
+    n_clouds = len(lens)
+    offs = ops.make_offsets(lens, DEV)
+    status = ops.new_status(DEV)
+    sub, sub_offs = ops.grid_subsample(G(pts), offs, n_clouds, dl, status)
+    want_sub, want_len = pre.grid_subsample(pts, lens, dl)
+    so = N(sub_offs)
+    assert np.array_equal(np.diff(so), want_len)
+    assert np.array_equal(N(sub)[:so[-1]], want_sub)            # bit-exact barycentres, canonical order
+    grid = ops.CellGrid(G(pts), offs, n_clouds, r * 1.0001, status)
+    i32, i64 = ops.ball_query(G(pts), offs, G(pts), offs, grid, K, r, q_order=grid.order)
+    want = pre.ball_query(pts, lens, pts, lens, K, r)
+    assert np.array_equal(N(i64), want) and np.array_equal(N(i32).astype(np.int64), want)
+    # strided query: coarse queries against fine supports, capacity-padded query buffer
+    p32, _ = ops.ball_query(sub, sub_offs, G(pts), offs, grid, K, r)
+    want_p = pre.ball_query(want_sub, want_len, pts, lens, K, r)
+    assert np.array_equal(N(p32)[:so[-1]].astype(np.int64), want_p)
+    assert int(status.item()) == 0
+
+
+def test_ball_query_dense_cluster_overflow_path():
+    """More hits than the per-warp staging buffer (384): the keep-K-smallest compaction must still
+    return the first K supports in index order."""
+    from oracle import pre
+    from regtr_b200 import ops
+    rng = np.random.default_rng(2)
+    pts = np.concatenate([rng.normal(size=(1500, 3)) * 0.01, rng.uniform(-1, 1, size=(500, 3))]).astype(np.float32)
+    pts = pts[rng.permutation(len(pts))]
+    lens = [len(pts)]
+    offs = ops.make_offsets(lens, DEV)
+    status = ops.new_status(DEV)
+    grid = ops.CellGrid(G(pts), offs, 1, 0.0626, status)
+    for K in (40, 50, 128):
+        _, i64 = ops.ball_query(G(pts), offs, G(pts), offs, grid, K, 0.0625)
+        assert np.array_equal(N(i64), pre.ball_query(pts, lens, pts, lens, K, 0.0625))
+
+
+def test_key_range_status_flag():
+    from regtr_b200 import ops
+    pts = np.array([[0, 0, 0], [5000.0, 0, 0]], dtype=np.float32)     # 5000 / 0.05 = 100000 cells
+    status = ops.new_status(DEV)
+    ops.grid_subsample(G(pts), ops.make_offsets([2], DEV), 1, 0.05, status)
+    assert int(status.item()) & 1
+
+
+# ---------------------------------------------------------------------- full forward
+
+def _run_model(cfg, sd, src, tgt):
+    from regtr_b200.regtr import RegTR
+    model = RegTR(cfg).to(DEV).eval()
+    model.load_state_dict(sd, strict=True)
+    batch = {'src_xyz': [G(s) for s in src], 'tgt_xyz': [G(t) for t in tgt]}
+    out = model(batch)
+    torch.cuda.synchronize()
+    return out, batch['kpconv_meta']
+
+
+@pytest.mark.parametrize('case', sorted(FORWARD_CASES))
+def test_forward_vs_reference_golden(case):
+    cfg, sd, src, tgt = make_case(case)
+    out, meta = _run_model(cfg, sd, src, tgt)
+    assert out['pose'].shape == (6, len(src), 3, 4)
+    check_forward_against_golden(out, meta, load_golden(case), len(src), feat_rtol=1e-4, corr_atol=1e-4,
+                                 logit_atol=2e-4, pose_atol=1e-4)
+
+
+def test_forward_3dmatch_full_size_vs_oracle():
+    """BASELINE config 2 (one ~20k-point pair): indices bit-exact vs the oracle pyramid, float stages
+    vs the oracle run on the same pyramid, pose within 1e-4."""
+    from oracle import pre, regtr_oracle as O
+    from regtr_b200.config import get_config
+    from regtr_b200.synthetic import make_3dmatch_pair
+    from regtr_b200.weights import random_state_dict
+    cfg = get_config('3dmatch')
+    sd = random_state_dict(cfg, 5)
+    p = make_3dmatch_pair(2000)
+    out, meta = _run_model(cfg, sd, [p['src_xyz']], [p['tgt_xyz']])
+    want = pre.preprocess(cfg, [p['src_xyz'], p['tgt_xyz']])
+    for key in ('points', 'neighbors', 'pools', 'upsamples', 'stack_lengths'):
+        for lvl, (a, b) in enumerate(zip(meta[key], want[key])):
+            assert np.array_equal(N(a), b), f'{key}[{lvl}]'
+    ref = O.forward(sd, cfg, [p['src_xyz']], [p['tgt_xyz']], meta=want)
+    for k, rtol in (('src_feat_un', 1e-4), ('tgt_feat_un', 1e-4), ('src_feat', 1e-4), ('tgt_feat', 1e-4)):
+        a, b = N(out[k][0]), ref[k][0].numpy()
+        assert np.abs(a - b).max() <= rtol * np.abs(b).max(), k
+    assert np.abs(N(out['src_kp_warped'][0]) - ref['src_kp_warped'][0].numpy()).max() <= 1e-4
+    assert np.abs(N(out['pose']) - ref['pose'].numpy()).max() <= 1e-4
+    # size-independent property: the pose is a proper rigid transform on every layer
+    R = N(out['pose'])[..., :3].astype(np.float64)
+    assert np.abs(R @ np.swapaxes(R, -1, -2) - np.eye(3)).max() <= 1e-5 and np.all(np.linalg.det(R) > 0)
+
+
+def test_forward_is_deterministic_and_batch_invariant():
+    """Same pair alone and inside a batch of 3 gives bit-identical indices and (near-)identical pose."""
+    from regtr_b200.config import get_config
+    from regtr_b200.synthetic import make_3dmatch_pair
+    from regtr_b200.weights import random_state_dict
+    cfg = get_config('3dmatch')
+    sd = random_state_dict(cfg, 6)
+    ps = [make_3dmatch_pair(2100 + i, 4000) for i in range(3)]
+    o1, m1 = _run_model(cfg, sd, [ps[1]['src_xyz']], [ps[1]['tgt_xyz']])
+    o1b, _ = _run_model(cfg, sd, [ps[1]['src_xyz']], [ps[1]['tgt_xyz']])
+    o3, m3 = _run_model(cfg, sd, [p['src_xyz'] for p in ps], [p['tgt_xyz'] for p in ps])
+    assert torch.equal(o1['pose'], o1b['pose'])
+    assert torch.equal(o1['src_kp'][0], o3['src_kp'][1])
+    assert float((o1['pose'][:, 0] - o3['pose'][:, 1]).abs().max()) <= 2e-5
