@@ -31,6 +31,18 @@ import torch  # noqa: E402
 
 WEIGHT_SEED = 2024
 POOL = 8          # distinct synthetic pairs rotated through the steps
+_T0 = time.time()
+
+
+def log(msg):
+    if int(os.environ.get('RANK', 0)) == 0:
+        print(f'[bench {time.time() - _T0:7.1f}s] {msg}', file=sys.stderr, flush=True)
+
+
+def cpu_threads():
+    """Threads for the CPU legs: all host cores up to 32 (beyond that the ATen ops of this workload,
+    ~1 ms each, slow down from fork/join overhead); reported as `cores`."""
+    return max(1, min(os.cpu_count() or 1, int(os.environ.get('REGTR_CPU_THREADS', 32))))
 
 
 def parse():
@@ -42,6 +54,8 @@ def parse():
     ap.add_argument('--config', type=int, default=2, help='BASELINE.json config id (2..5)')
     ap.add_argument('--pairs', type=int, default=None, help='pairs per GPU per step (default: from config)')
     ap.add_argument('--cpu-baseline', type=int, default=1, help='time the CPU port beside the GPU run (N=1 only)')
+    ap.add_argument('--checks', type=int, default=1, help='report pose error vs the oracle on one pair')
+    ap.add_argument('--graph', type=int, default=1, help='1: CUDA-graph executor (GraphedRegTR); 0: eager forward')
     return ap.parse_args()
 
 
@@ -131,7 +145,7 @@ def cpu_forward_fn(cfg, sd):
 
 
 def time_cpu(cfg, sd, pool, n_pairs, warm=1):
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     run, pre_kind = cpu_forward_fn(cfg, sd)
     for i in range(warm):
@@ -177,8 +191,9 @@ def run_reference(args, rank, world):
     B = pairs_per_gpu(args)
     pool = make_pool(args.config, min(POOL, max(2, args.steps)))
     run, pre_kind = cpu_forward_fn(cfg, sd)
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
+    log(f'reference arm: {cores} threads of {os.cpu_count()} cores')
     for i in range(max(args.warmup, 1)):
         run(*pool[i % len(pool)])
     # each step = a bounded sample of the workload: ONE pair (the workload has B*N pairs/step)
@@ -211,7 +226,7 @@ def main():
     from regtr_b200 import ops
     from regtr_b200.config import get_config
     from regtr_b200.dist import gather_poses
-    from regtr_b200.regtr import RegTR
+    from regtr_b200.regtr import GraphedRegTR, RegTR
     from regtr_b200.weights import random_state_dict
 
     assert torch.cuda.is_available(), 'bench.py --impl b200 needs a CUDA device (no CPU fallback)'
@@ -228,6 +243,7 @@ def main():
     sd = random_state_dict(cfg, WEIGHT_SEED)
     model = RegTR(cfg).to(dev).eval()
     model.load_state_dict(sd, strict=True)
+    runner = GraphedRegTR(model) if args.graph else model      # the public call a user makes
 
     # rank-local pool of distinct pairs (generated rank-locally)
     n_pool = max(POOL, B)
@@ -248,16 +264,19 @@ def main():
 
     def device_step(step):
         batch, _ = batch_at(step, resident)
-        out = model(batch)
+        out = runner(batch)
         return gather_poses(out['pose'], B * world) if world > 1 else out['pose']
 
     def e2e_step(step):
         batch, ids = batch_at(step, host)
-        batch = {k: [t.to(dev, non_blocking=True) for t in v] for k, v in batch.items()}
-        out = model(batch)
-        pose = gather_poses(out['pose'], B * world) if world > 1 else out['pose']
-        return pose.cpu(), ids
+        if not args.graph:
+            batch = {k: [t.to(dev, non_blocking=True) for t in v] for k, v in batch.items()}
+        out = runner(batch)                     # graph executor: packs the host clouds, one H2D copy
+        if world > 1:
+            return gather_poses(out['pose'], B * world).cpu(), ids
+        return (out['pose_host'] if 'pose_host' in out else out['pose'].cpu()), ids
 
+    log(f'pool ready ({n_pool} pairs, {sum(len(a) + len(b) for a, b in pool) // n_pool} pts/pair); warm-up')
     # ---------------- warm-up
     for i in range(W):
         device_step(i)
@@ -278,6 +297,7 @@ def main():
     barrier()
     launches = ops.LAUNCHES - launches0
     t_dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    log(f'device-resident: {t_dev_ms / K:.3f} ms/step')
 
     # ---------------- end-to-end: host buffers in, pose on the host out
     for i in range(2):
@@ -297,6 +317,7 @@ def main():
     barrier()
     t_e2e_ms = sum(a.elapsed_time(b) for a, b in evs)
     clocks = sampler.stop() if sampler else None
+    log(f'e2e: {t_e2e_ms / K:.3f} ms/step; clocks {clocks}')
 
     # ---------------- max over ranks
     t = torch.tensor([t_dev_ms, t_e2e_ms], dtype=torch.float64, device=dev)
@@ -326,11 +347,13 @@ def main():
     # ---------------- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and args.cpu_baseline:
+        log('cpu baseline ...')
         cpu, _ = time_cpu(cfg, sd, pool, n_pairs=3)
+        log(f'cpu baseline {cpu["value"]:.3f} pairs/s on {cpu["cores"]} threads')
 
     # ---------------- pose error vs the oracle on one pair (reported, also covered by tests/)
     pose_err = None
-    if rank == 0:
+    if rank == 0 and args.checks:
         try:
             from oracle import pre, regtr_oracle
             s, tg = pool[0]
@@ -349,7 +372,8 @@ def main():
             dtype='f32', data='synthetic',
             config=dict(workload=workload_name(args, B), pairs_per_gpu_per_step=B,
                         parallelism=f'pair-level data parallel x{world}', l2_flush_between_steps=True,
-                        weights='seeded random init (no pretrained weights offline)', precision_mode='fp32 parity'),
+                        weights='seeded random init (no pretrained weights offline)', precision_mode='fp32 parity',
+                        executor='cuda-graph (GraphedRegTR)' if args.graph else 'eager'),
             e2e=dict(value=pairs / (t_e2e_ms * 1e-3), unit='pairs/s', h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h, ms_per_step=t_e2e_ms / K),
             gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu,

@@ -38,6 +38,7 @@ extern "C" {
 #define REGTR_ERR_CUBLAS (-4)
 
 #define REGTR_STATUS_KEY_RANGE 1u /* a voxel / cell coordinate left the 16-bit key range */
+#define REGTR_STATUS_CAPACITY 2u  /* a capacity-bounded output (sub-sampled level) overflowed; results truncated */
 
 int regtr_version(void);                 /* ABI version, currently 1 */
 const char* regtr_build_info(void);      /* host pointer: arch + compile flags string */
@@ -49,11 +50,13 @@ const char* regtr_build_info(void);      /* host pointer: arch + compile flags s
  * i.e. MinkowskiEngine 0.5.4 SparseTensor(UNWEIGHTED_AVERAGE)) with the deterministic
  * rules of DESIGN.md: voxel = floor(p / dl) (IEEE fp32 division), output ordered by
  * ascending (cloud, vx, vy, vz), barycentre = fp32 sum in ascending input index / count.
- * xyz (n_cap,3) f32; offs (n_clouds+1) i32; out_xyz (n_cap,3); out_offs (n_clouds+1).
+ * xyz (n_cap,3) f32; offs (n_clouds+1) i32; out_xyz (out_cap,3); out_offs (n_clouds+1).
+ * out_cap may be smaller than n_cap (static-shape pipelines): on overflow the output is
+ * truncated memory-safely and REGTR_STATUS_CAPACITY is raised.
  * status: device uint32 word, OR-ed with REGTR_STATUS_* on data-dependent errors. */
 size_t regtr_grid_subsample_ws_bytes(int n_cap);
 int regtr_grid_subsample(const float* xyz, const int32_t* offs, int n_clouds, int n_cap, float dl,
-                         float* out_xyz, int32_t* out_offs, uint32_t* status,
+                         float* out_xyz, int out_cap, int32_t* out_offs, uint32_t* status,
                          void* ws, size_t ws_bytes, void* stream);
 
 /* Uniform cell list over a stacked point set (search structure for regtr_ball_query).
@@ -72,8 +75,9 @@ int regtr_cellgrid_build(const float* xyz, const int32_t* offs, int n_clouds, in
  * ((dx*dx + dy*dy) + dz*dz) < r*r in fp32 without FMA contraction; pad with the total
  * support count.  `s_grid` must have been built over (s, s_offs) with capacity s_cap and
  * cell >= radius.
- * q_order (optional, nq_cap): processing order of the queries.  out_idx32 / out_idx64
- * (nq_cap,K): either may be NULL. */
+ * q_order (optional, nq_cap): processing order of the queries (a permutation of [0,nq_cap)).
+ * out_idx32 / out_idx64 (nq_cap,K): either may be NULL; rows of capacity padding
+ * (>= q_offs[n_clouds]) are filled with the shadow index. */
 int regtr_ball_query(const float* q, const int32_t* q_offs, const int32_t* q_order,
                      const float* s, const int32_t* s_offs, const void* s_grid,
                      int n_clouds, int nq_cap, int s_cap, int K, float radius,
@@ -86,23 +90,27 @@ int regtr_ball_query(const float* q, const int32_t* q_offs, const int32_t* q_ord
  *   out[n] = (1/max(1,#{k: sum_c x[idx[n,k]] > 0})) * sum_p (sum_k h(n,k,p) x[idx[n,k]]) W[p]
  *   h = max(0, 1 - |s[idx[n,k]] - q[n] - kp[p]| / extent); idx == Ns is the shadow neighbour.
  * q (Nq,3) s (Ns,3) idx (Nq,K) i32, x (Ns,Cin) f32, W (P,Cin,Cout) f32, kp (P,3), out (Nq,Cout).
- * P must be 15.  Cin in {1..16} or a multiple of 32 up to 256.
+ * P must be 15.  Cin in {1..16} or 32/64/128/256.
+ * nq_dev / ns_dev (optional, device int32): actual query / support counts when Nq / Ns are
+ * capacities (static-shape pipelines); rows >= *nq_dev produce zeros, the shadow index is *ns_dev.
  * ws: regtr_kpconv_ws_bytes(Nq, Ns, Cin) bytes (aggregated features + row flags). */
 size_t regtr_kpconv_ws_bytes(int Nq, int Ns, int Cin);
 int regtr_kpconv_fwd(const float* q, const float* s, const int32_t* idx, const float* x,
-                     const float* W, const float* kp, int Nq, int Ns, int K, int Cin, int Cout,
+                     const float* W, const float* kp, int Nq, int Ns, const int32_t* nq_dev,
+                     const int32_t* ns_dev, int K, int Cin, int Cout,
                      float extent, float* out, void* ws, size_t ws_bytes, void* stream);
 
 /* Gather + influence + aggregation stage alone: wf (Nq, 15*Cin), already divided by the
  * neighbour count.  (The HBM-bound "neighbour gather" kernel of the north star.) */
 int regtr_kpconv_aggregate(const float* q, const float* s, const int32_t* idx, const float* x,
-                           const float* kp, int Nq, int Ns, int K, int Cin, float extent,
+                           const float* kp, int Nq, int Ns, const int32_t* nq_dev, const int32_t* ns_dev,
+                           int K, int Cin, float extent,
                            float* wf, uint8_t* rowflag_ws, void* stream);
 
 /* max over the K gathered rows with a zero shadow row.  Replaces max_pool
  * (kpconv_blocks.py:127-143).  x (Ns,C), idx (Nq,K) i32 -> out (Nq,C). */
-int regtr_max_pool(const float* x, const int32_t* idx, int Nq, int Ns, int K, int C, float* out,
-                   void* stream);
+int regtr_max_pool(const float* x, const int32_t* idx, int Nq, int Ns, const int32_t* ns_dev, int K, int C,
+                   float* out, void* stream);
 
 /* Per-cloud InstanceNorm1d(affine=False, eps) over the points of each cloud, optional
  * residual add, optional LeakyReLU.  Replaces BatchNormBlock.forward + nn.LeakyReLU
@@ -127,6 +135,11 @@ int regtr_pos_embed_sine(const float* xyz, int n, const float* dim_t, int n_freq
  * 194-196, 213-215, 232).  Any of y / y_pos may be NULL. */
 int regtr_layernorm_pos(const float* x, const float* gamma, const float* beta, const float* pos,
                         int n, int E, float eps, float* y, float* y_pos, void* stream);
+
+/* Device-side attention problem table for a (src x B, tgt x B) token stack with cloud offsets
+ * offs (2B+1): plan (4, 2B) i32 rows = q_start, q_len, cross k_start, cross k_len (the cross
+ * partner of src_b is tgt_b and vice versa; regtr.py:156-166's key-padding masks made explicit). */
+int regtr_attention_plan(const int32_t* offs, int B, int32_t* plan, void* stream);
 
 /* Variable-length multi-head attention core, fp32:  O = softmax(Q K^T * scale) V per head.
  * Replaces the attention core of nn.MultiheadAttention as called at

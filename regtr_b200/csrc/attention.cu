@@ -116,7 +116,28 @@ k_mha_fp32(const float* __restrict__ Q, int ldq, const float* __restrict__ Kp, i
     }
 }
 
+// plan[0..4)[c]: q_start, q_len, cross k_start, cross k_len for cloud c of a (src x B, tgt x B) stack.
+__global__ void k_attention_plan(const int32_t* __restrict__ offs, int B, int32_t* __restrict__ plan) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n2 = 2 * B;
+    if (c >= n2) return;
+    const int o = c < B ? c + B : c - B;
+    plan[0 * n2 + c] = offs[c];
+    plan[1 * n2 + c] = offs[c + 1] - offs[c];
+    plan[2 * n2 + c] = offs[o];
+    plan[3 * n2 + c] = offs[o + 1] - offs[o];
+}
+
 }  // namespace
+
+extern "C" int regtr_attention_plan(const int32_t* offs, int B, int32_t* plan, void* stream_) {
+    if (B < 0) return REGTR_ERR_ARG;
+    if (B == 0) return REGTR_OK;
+    if (!offs || !plan) return REGTR_ERR_ARG;
+    k_attention_plan<<<regtr_cdiv(2 * B, 128), 128, 0, (cudaStream_t)stream_>>>(offs, B, plan);
+    REGTR_CHECK_LAUNCH();
+    return REGTR_OK;
+}
 
 extern "C" int regtr_mha_varlen_fwd(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
                                     float* O, int ldo, const int32_t* q_start, const int32_t* q_len,

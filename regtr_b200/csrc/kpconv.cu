@@ -82,7 +82,8 @@ template <int VEC, int UNROLL>
 __global__ void __launch_bounds__(AGG_WARPS * 32)
 k_kpconv_agg(const float* __restrict__ q, const float* __restrict__ s, const int32_t* __restrict__ idx,
              const float* __restrict__ x, const uint8_t* __restrict__ flags, const float* __restrict__ kp,
-             int Nq, int Ns, int K, float extent, float* __restrict__ wf) {
+             int Nq, int Ns, const int32_t* __restrict__ nq_dev, const int32_t* __restrict__ ns_dev, int K,
+             float extent, float* __restrict__ wf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int CIN = VEC * 32;
     constexpr int NV4 = VEC >= 4 ? VEC / 4 : 1;          // float4 loads per lane
@@ -95,6 +96,12 @@ k_kpconv_agg(const float* __restrict__ q, const float* __restrict__ s, const int
     __syncthreads();
     const int qi = blockIdx.x * AGG_WARPS + warp;
     if (qi >= Nq) return;
+    if (ns_dev) Ns = min(Ns, *ns_dev);
+    if (nq_dev && qi >= *nq_dev) {               // capacity padding row: zeros
+        float* o = wf + (size_t)qi * (KP * CIN);
+        for (int t = lane; t < KP * CIN; t += 32) o[t] = 0.f;
+        return;
+    }
 
     int n_valid, n_counted;
     stage_neighbours(s, idx + (size_t)qi * K, flags, kp_s, q[3 * qi], q[3 * qi + 1], q[3 * qi + 2], Ns, K, extent,
@@ -161,15 +168,21 @@ k_kpconv_agg(const float* __restrict__ q, const float* __restrict__ s, const int
 __global__ void __launch_bounds__(AGG_WARPS * 32)
 k_kpconv_agg_small(const float* __restrict__ q, const float* __restrict__ s, const int32_t* __restrict__ idx,
                    const float* __restrict__ x, const uint8_t* __restrict__ flags, const float* __restrict__ kp,
-                   int Nq, int Ns, int K, int Cin, float extent, float* __restrict__ wf) {
+                   int Nq, int Ns, const int32_t* __restrict__ nq_dev, const int32_t* __restrict__ ns_dev, int K, int Cin,
+                   float extent, float* __restrict__ wf) {
     __shared__ float kp_s[48];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < 3 * KP) kp_s[threadIdx.x] = kp[threadIdx.x];
     __syncthreads();
     const int qi = blockIdx.x * AGG_WARPS + warp;
     if (qi >= Nq) return;
-    const float qx = q[3 * qi], qy = q[3 * qi + 1], qz = q[3 * qi + 2];
+    if (ns_dev) Ns = min(Ns, *ns_dev);
     float* out = wf + (size_t)qi * (KP * Cin);
+    if (nq_dev && qi >= *nq_dev) {
+        for (int t = lane; t < KP * Cin; t += 32) out[t] = 0.f;
+        return;
+    }
+    const float qx = q[3 * qi], qy = q[3 * qi + 1], qz = q[3 * qi + 2];
     int counted = 0;
     for (int c = 0; c < Cin; ++c) {
         float accp[KP];
@@ -205,11 +218,12 @@ k_kpconv_agg_small(const float* __restrict__ q, const float* __restrict__ s, con
 }
 
 // out[q, c] = max(0-shadow, x[idx[q,k], c]) ; 4 channels per thread.
-__global__ void k_max_pool(const float* __restrict__ x, const int32_t* __restrict__ idx, int Nq, int Ns, int K, int C,
-                           float* __restrict__ out) {
+__global__ void k_max_pool(const float* __restrict__ x, const int32_t* __restrict__ idx, int Nq, int Ns,
+                           const int32_t* __restrict__ ns_dev, int K, int C, float* __restrict__ out) {
     const int c4 = C >> 2;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)Nq * c4) return;
+    if (ns_dev) Ns = min(Ns, *ns_dev);
     const int qi = (int)(t / c4), cc = (int)(t % c4);
     float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     for (int k = 0; k < K; ++k) {
@@ -221,10 +235,11 @@ __global__ void k_max_pool(const float* __restrict__ x, const int32_t* __restric
     reinterpret_cast<float4*>(out + (size_t)qi * C)[cc] = m;
 }
 
-__global__ void k_max_pool_scalar(const float* __restrict__ x, const int32_t* __restrict__ idx, int Nq, int Ns, int K,
-                                  int C, float* __restrict__ out) {
+__global__ void k_max_pool_scalar(const float* __restrict__ x, const int32_t* __restrict__ idx, int Nq, int Ns,
+                                  const int32_t* __restrict__ ns_dev, int K, int C, float* __restrict__ out) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)Nq * C) return;
+    if (ns_dev) Ns = min(Ns, *ns_dev);
     const int qi = (int)(t / C), c = (int)(t % C);
     float m = -INFINITY;
     for (int k = 0; k < K; ++k) {
@@ -257,7 +272,8 @@ size_t agg_smem_bytes(int K) {
 
 template <int VEC, int UNROLL>
 int launch_agg(const float* q, const float* s, const int32_t* idx, const float* x, const uint8_t* flags,
-               const float* kp, int Nq, int Ns, int K, float extent, float* wf, cudaStream_t st) {
+               const float* kp, int Nq, int Ns, const int32_t* nq_dev, const int32_t* ns_dev, int K, float extent,
+               float* wf, cudaStream_t st) {
     const size_t smem = agg_smem_bytes(K);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_kpconv_agg<VEC, UNROLL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -265,7 +281,7 @@ int launch_agg(const float* q, const float* s, const int32_t* idx, const float* 
         if (e != cudaSuccess) return -(1000 + (int)e);
     }
     k_kpconv_agg<VEC, UNROLL><<<regtr_cdiv(Nq, AGG_WARPS), AGG_WARPS * 32, smem, st>>>(q, s, idx, x, flags, kp, Nq, Ns,
-                                                                                     K, extent, wf);
+                                                                                     nq_dev, ns_dev, K, extent, wf);
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
 }
@@ -280,8 +296,8 @@ size_t regtr_kpconv_ws_bytes(int Nq, int Ns, int Cin) {
 }
 
 int regtr_kpconv_aggregate(const float* q, const float* s, const int32_t* idx, const float* x, const float* kp,
-                           int Nq, int Ns, int K, int Cin, float extent, float* wf, uint8_t* rowflag_ws,
-                           void* stream_) {
+                           int Nq, int Ns, const int32_t* nq_dev, const int32_t* ns_dev, int K, int Cin, float extent,
+                           float* wf, uint8_t* rowflag_ws, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (Nq < 0 || Ns < 0 || K <= 0 || K > 128 || Cin <= 0 || !(extent > 0.f)) return REGTR_ERR_ARG;
     if (!(Cin <= 16 || (Cin % 32 == 0 && Cin <= 256 && (Cin / 32 == 1 || Cin / 32 == 2 || Cin / 32 == 4 || Cin / 32 == 8))))
@@ -294,22 +310,22 @@ int regtr_kpconv_aggregate(const float* q, const float* s, const int32_t* idx, c
     }
     if (Cin <= 16) {
         k_kpconv_agg_small<<<regtr_cdiv(Nq, AGG_WARPS), AGG_WARPS * 32, 0, st>>>(q, s, idx, x, rowflag_ws, kp, Nq, Ns,
-                                                                                K, Cin, extent, wf);
+                                                                                nq_dev, ns_dev, K, Cin, extent, wf);
         REGTR_CHECK_LAUNCH();
         return REGTR_OK;
     }
     switch (Cin / 32) {
-        case 1: return launch_agg<1, 4>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, K, extent, wf, st);
-        case 2: return launch_agg<2, 4>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, K, extent, wf, st);
-        case 4: return launch_agg<4, 4>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, K, extent, wf, st);
-        case 8: return launch_agg<8, 2>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, K, extent, wf, st);
+        case 1: return launch_agg<1, 4>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, extent, wf, st);
+        case 2: return launch_agg<2, 4>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, extent, wf, st);
+        case 4: return launch_agg<4, 4>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, extent, wf, st);
+        case 8: return launch_agg<8, 2>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, extent, wf, st);
     }
     return REGTR_ERR_UNSUPPORTED;
 }
 
 int regtr_kpconv_fwd(const float* q, const float* s, const int32_t* idx, const float* x, const float* W,
-                     const float* kp, int Nq, int Ns, int K, int Cin, int Cout, float extent, float* out, void* ws,
-                     size_t ws_bytes, void* stream_) {
+                     const float* kp, int Nq, int Ns, const int32_t* nq_dev, const int32_t* ns_dev, int K, int Cin,
+                     int Cout, float extent, float* out, void* ws, size_t ws_bytes, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (Cout <= 0 || Cin <= 0 || Nq < 0 || Ns < 0) return REGTR_ERR_ARG;
     if (Nq == 0) return REGTR_OK;
@@ -317,7 +333,7 @@ int regtr_kpconv_fwd(const float* q, const float* s, const int32_t* idx, const f
     if (ws_bytes < regtr_kpconv_ws_bytes(Nq, Ns, Cin)) return REGTR_ERR_WORKSPACE;
     float* wf = (float*)ws;
     uint8_t* flags = (uint8_t*)ws + regtr_align(sizeof(float) * (size_t)Nq * KP * (size_t)Cin);
-    int rc = regtr_kpconv_aggregate(q, s, idx, x, kp, Nq, Ns, K, Cin, extent, wf, flags, stream_);
+    int rc = regtr_kpconv_aggregate(q, s, idx, x, kp, Nq, Ns, nq_dev, ns_dev, K, Cin, extent, wf, flags, stream_);
     if (rc != REGTR_OK) return rc;
     // out[Nq,Cout] = wf[Nq,15*Cin] @ W[15*Cin,Cout]  (row-major)  ==  column-major out^T = W^T wf^T
     cublasHandle_t h = get_handle();
@@ -331,15 +347,16 @@ int regtr_kpconv_fwd(const float* q, const float* s, const int32_t* idx, const f
     return REGTR_OK;
 }
 
-int regtr_max_pool(const float* x, const int32_t* idx, int Nq, int Ns, int K, int C, float* out, void* stream_) {
+int regtr_max_pool(const float* x, const int32_t* idx, int Nq, int Ns, const int32_t* ns_dev, int K, int C,
+                   float* out, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (Nq < 0 || Ns < 0 || K <= 0 || C <= 0) return REGTR_ERR_ARG;
     if (Nq == 0) return REGTR_OK;
     if (!x || !idx || !out) return REGTR_ERR_ARG;
     if (C % 4 == 0) {
-        k_max_pool<<<regtr_cdiv((long long)Nq * (C / 4), 256), 256, 0, st>>>(x, idx, Nq, Ns, K, C, out);
+        k_max_pool<<<regtr_cdiv((long long)Nq * (C / 4), 256), 256, 0, st>>>(x, idx, Nq, Ns, ns_dev, K, C, out);
     } else {
-        k_max_pool_scalar<<<regtr_cdiv((long long)Nq * C, 256), 256, 0, st>>>(x, idx, Nq, Ns, K, C, out);
+        k_max_pool_scalar<<<regtr_cdiv((long long)Nq * C, 256), 256, 0, st>>>(x, idx, Nq, Ns, ns_dev, K, C, out);
     }
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;

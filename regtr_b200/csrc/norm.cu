@@ -7,12 +7,13 @@
 
 namespace {
 
-constexpr int IN_CH = 1024;   // rows per statistics chunk
-constexpr int IN_TY = 8;
+constexpr int IN_CH = 128;    // rows per statistics chunk
+constexpr int IN_TY = 8;      // row lanes per block (block = 32 x 8 threads, 4 channels per thread)
+constexpr int IN_CT = 128;    // channels per block
 
 // chunk id -> (cloud, first row, last row) ; chunks never straddle clouds.
 __device__ __forceinline__ bool chunk_of(const int32_t* __restrict__ offs, int n_clouds, int chunk, int& cloud,
-                                         int& r0, int& r1, int& first_chunk, int& n_chunks) {
+                                         int& r0, int& r1) {
     int acc = 0;
     for (int c = 0; c < n_clouds; ++c) {
         const int a = offs[c], b = offs[c + 1];
@@ -21,8 +22,6 @@ __device__ __forceinline__ bool chunk_of(const int32_t* __restrict__ offs, int n
             cloud = c;
             r0 = a + (chunk - acc) * IN_CH;
             r1 = min(r0 + IN_CH, b);
-            first_chunk = acc;
-            n_chunks = nc;
             return true;
         }
         acc += nc;
@@ -30,63 +29,98 @@ __device__ __forceinline__ bool chunk_of(const int32_t* __restrict__ offs, int n
     return false;
 }
 
-// partial[chunk][c] = (sum, sum of squares) in fp64 over the chunk's rows.
+// partial[chunk][c] = (sum, sum of squares) in fp64 over the chunk's rows.  C % 4 == 0.
 __global__ void __launch_bounds__(32 * IN_TY)
 k_in_stats(const float* __restrict__ x, const int32_t* __restrict__ offs, int n_clouds, int C,
            double2* __restrict__ partial) {
+    __shared__ double red[IN_TY][32][8];
+    int cloud, r0, r1;
+    if (!chunk_of(offs, n_clouds, blockIdx.x, cloud, r0, r1)) return;
+    const int c = blockIdx.y * IN_CT + threadIdx.x * 4;
+    double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    if (c < C) {
+        for (int r = r0 + threadIdx.y; r < r1; r += IN_TY * 4) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int rr = r + u * IN_TY;
+                v[u] = rr < r1 ? __ldg(reinterpret_cast<const float4*>(x + (size_t)rr * C + c))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double a0 = v[u].x, a1 = v[u].y, a2 = v[u].z, a3 = v[u].w;
+                s[0] += a0; s[1] += a1; s[2] += a2; s[3] += a3;
+                ss[0] += a0 * a0; ss[1] += a1 * a1; ss[2] += a2 * a2; ss[3] += a3 * a3;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[threadIdx.y][threadIdx.x][j] = s[j]; red[threadIdx.y][threadIdx.x][4 + j] = ss[j]; }
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        for (int t = 1; t < IN_TY; ++t)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s[j] += red[t][threadIdx.x][j]; ss[j] += red[t][threadIdx.x][4 + j]; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) partial[(size_t)blockIdx.x * C + c + j] = make_double2(s[j], ss[j]);
+    }
+}
+
+// stats[cloud][c] = (mean, 1/sqrt(var+eps)); the cloud's chunk partials are summed by 8 row lanes
+// (fixed assignment) and combined in a fixed order: deterministic, no atomics.
+__global__ void __launch_bounds__(32 * IN_TY)
+k_in_finalize(const int32_t* __restrict__ offs, int n_clouds, int C, float eps, const double2* __restrict__ partial,
+              float2* __restrict__ stats) {
     __shared__ double2 red[IN_TY][32];
-    int cloud, r0, r1, fc, nc;
-    if (!chunk_of(offs, n_clouds, blockIdx.x, cloud, r0, r1, fc, nc)) return;
+    const int cloud = blockIdx.x;
     const int c = blockIdx.y * 32 + threadIdx.x;
+    int first = 0;
+    for (int k = 0; k < cloud; ++k) first += (offs[k + 1] - offs[k] + IN_CH - 1) / IN_CH;
+    const int n = offs[cloud + 1] - offs[cloud];
+    const int nc = (n + IN_CH - 1) / IN_CH;
     double s = 0.0, ss = 0.0;
     if (c < C) {
-        for (int r = r0 + threadIdx.y; r < r1; r += IN_TY) {
-            const double v = (double)x[(size_t)r * C + c];
-            s += v;
-            ss += v * v;
+        for (int t = threadIdx.y; t < nc; t += IN_TY) {
+            const double2 p = partial[(size_t)(first + t) * C + c];
+            s += p.x; ss += p.y;
         }
     }
     red[threadIdx.y][threadIdx.x] = make_double2(s, ss);
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
         for (int t = 1; t < IN_TY; ++t) { s += red[t][threadIdx.x].x; ss += red[t][threadIdx.x].y; }
-        partial[(size_t)blockIdx.x * C + c] = make_double2(s, ss);
+        const double dn = n > 0 ? (double)n : 1.0;
+        const double mean = s / dn;
+        double var = ss / dn - mean * mean;          // biased variance (InstanceNorm)
+        var = var > 0.0 ? var : 0.0;
+        stats[(size_t)cloud * C + c] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
     }
 }
 
-// out = act(norm(x) + res) on the chunk's rows; the cloud's statistics are re-reduced from
-// its chunk partials in a fixed order (deterministic, no atomics).
-__global__ void __launch_bounds__(32 * IN_TY)
-k_in_apply(const float* x, const int32_t* __restrict__ offs, int n_clouds, int C, float eps,
-           const double2* __restrict__ partial, const float* res, float slope, float* out) {
-    __shared__ float s_mean[32], s_rstd[32];
-    int cloud, r0, r1, fc, nc;
-    if (!chunk_of(offs, n_clouds, blockIdx.x, cloud, r0, r1, fc, nc)) return;
-    const int c = blockIdx.y * 32 + threadIdx.x;
-    if (threadIdx.y == 0 && c < C) {
-        double s = 0.0, ss = 0.0;
-        for (int t = 0; t < nc; ++t) {
-            const double2 p = partial[(size_t)(fc + t) * C + c];
-            s += p.x;
-            ss += p.y;
-        }
-        const double n = (double)(offs[cloud + 1] - offs[cloud]);
-        const double mean = s / n;
-        double var = ss / n - mean * mean;          // biased variance (InstanceNorm)
-        var = var > 0.0 ? var : 0.0;
-        s_mean[threadIdx.x] = (float)mean;
-        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+// out = act((x - mean) * rstd + res), float4 per thread; rows beyond offs[n_clouds] are zeroed.
+__global__ void k_in_apply(const float* x, const int32_t* __restrict__ offs, int n_clouds, int n_cap, int C,
+                           const float2* __restrict__ stats, const float* res, float slope, float* out) {
+    const int c4n = C >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n_cap * c4n) return;
+    const int r = (int)(t / c4n), c = (int)(t % c4n) * 4;
+    const size_t o = (size_t)r * C + c;
+    if (r >= offs[n_clouds]) { *reinterpret_cast<float4*>(out + o) = make_float4(0.f, 0.f, 0.f, 0.f); return; }
+    const int cloud = regtr_cloud_of(offs, n_clouds, r);
+    const float4 v = *reinterpret_cast<const float4*>(x + o);
+    const float4 st01 = *reinterpret_cast<const float4*>(stats + (size_t)cloud * C + c);
+    const float4 st23 = *reinterpret_cast<const float4*>(stats + (size_t)cloud * C + c + 2);
+    float y[4] = {(v.x - st01.x) * st01.y, (v.y - st01.z) * st01.w, (v.z - st23.x) * st23.y, (v.w - st23.z) * st23.w};
+    if (res) {
+        const float4 rv = *reinterpret_cast<const float4*>(res + o);
+        y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
     }
-    __syncthreads();
-    if (c >= C) return;
-    const float mean = s_mean[threadIdx.x], rstd = s_rstd[threadIdx.x];
-    for (int r = r0 + threadIdx.y; r < r1; r += IN_TY) {
-        const size_t o = (size_t)r * C + c;
-        float v = (x[o] - mean) * rstd;
-        if (res) v += res[o];
-        if (slope >= 0.f) v = v > 0.f ? v : v * slope;
-        out[o] = v;
+    if (slope >= 0.f) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = y[j] > 0.f ? y[j] : y[j] * slope;
     }
+    *reinterpret_cast<float4*>(out + o) = make_float4(y[0], y[1], y[2], y[3]);
 }
 
 // One warp per row; E <= 1024, multiple of 32.
@@ -135,23 +169,31 @@ __global__ void k_pos_embed_sine(const float* __restrict__ xyz, int n, const flo
 
 extern "C" {
 
+static inline int in_chunks(int n_cap, int n_clouds) { return regtr_cdiv(n_cap > 0 ? n_cap : 1, IN_CH) + n_clouds; }
+
 size_t regtr_instnorm_ws_bytes(int n_cap, int n_clouds, int C) {
-    const size_t chunks = (size_t)regtr_cdiv(n_cap > 0 ? n_cap : 1, IN_CH) + (size_t)(n_clouds > 0 ? n_clouds : 1);
-    return regtr_align(chunks * (size_t)(C > 0 ? C : 1) * sizeof(double2));
+    const size_t c = (size_t)(C > 0 ? C : 1), nc = (size_t)(n_clouds > 0 ? n_clouds : 1);
+    return regtr_align((size_t)in_chunks(n_cap, (int)nc) * c * sizeof(double2)) + regtr_align(nc * c * sizeof(float2));
 }
 
 int regtr_instnorm_act(const float* x, const int32_t* offs, int n_clouds, int n_cap, int C, float eps,
                        const float* res, float slope, float* out, void* ws, size_t ws_bytes, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (!offs || n_clouds <= 0 || n_cap < 0 || C <= 0) return REGTR_ERR_ARG;
+    if (C % 4 != 0) return REGTR_ERR_UNSUPPORTED;
     if (n_cap == 0) return REGTR_OK;
     if (!x || !out || !ws) return REGTR_ERR_ARG;
     if (ws_bytes < regtr_instnorm_ws_bytes(n_cap, n_clouds, C)) return REGTR_ERR_WORKSPACE;
-    const int chunks = regtr_cdiv(n_cap, IN_CH) + n_clouds;
-    dim3 grid(chunks, regtr_cdiv(C, 32)), block(32, IN_TY);
-    k_in_stats<<<grid, block, 0, st>>>(x, offs, n_clouds, C, (double2*)ws);
+    const int chunks = in_chunks(n_cap, n_clouds);
+    double2* partial = (double2*)ws;
+    float2* stats = (float2*)((char*)ws + regtr_align((size_t)chunks * C * sizeof(double2)));
+    dim3 block(32, IN_TY);
+    k_in_stats<<<dim3(chunks, regtr_cdiv(C, IN_CT)), block, 0, st>>>(x, offs, n_clouds, C, partial);
     REGTR_CHECK_LAUNCH();
-    k_in_apply<<<grid, block, 0, st>>>(x, offs, n_clouds, C, eps, (const double2*)ws, res, slope, out);
+    k_in_finalize<<<dim3(n_clouds, regtr_cdiv(C, 32)), block, 0, st>>>(offs, n_clouds, C, eps, partial, stats);
+    REGTR_CHECK_LAUNCH();
+    k_in_apply<<<regtr_cdiv((long long)n_cap * (C / 4), 256), 256, 0, st>>>(x, offs, n_clouds, n_cap, C, stats, res,
+                                                                            slope, out);
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
 }

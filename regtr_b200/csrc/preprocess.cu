@@ -59,11 +59,12 @@ __global__ void k_head_flags(const unsigned long long* __restrict__ skeys, int n
 // (the radix sort is stable, so members appear in that order), then one IEEE division.
 __global__ void k_voxel_mean(const float* __restrict__ xyz, const unsigned long long* __restrict__ skeys,
                              const int32_t* __restrict__ sidx, const int32_t* __restrict__ rank, int n_cap,
-                             float* __restrict__ out_xyz) {
+                             int out_cap, float* __restrict__ out_xyz, uint32_t* status) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_cap) return;
     const unsigned long long k = skeys[j];
     if (k == KEY_PAD || (j > 0 && skeys[j - 1] == k)) return;
+    if (rank[j] >= out_cap) { atomicOr(status, REGTR_STATUS_CAPACITY); return; }
     float sx = 0.f, sy = 0.f, sz = 0.f;
     int cnt = 0;
     for (int t = j; t < n_cap && skeys[t] == k; ++t) {
@@ -91,12 +92,12 @@ __device__ __forceinline__ int lower_bound_u64(const unsigned long long* __restr
 
 // out_offs[c] = number of voxels whose key is below cloud c's first key.
 __global__ void k_cloud_offsets(const unsigned long long* __restrict__ skeys, const int32_t* __restrict__ rank,
-                                int n_cap, int n_clouds, int32_t* __restrict__ out_offs) {
+                                int n_cap, int n_clouds, int out_cap, int32_t* __restrict__ out_offs) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c > n_clouds) return;
-    if (c == n_clouds) { out_offs[c] = rank[n_cap]; return; }
+    if (c == n_clouds) { out_offs[c] = min(rank[n_cap], out_cap); return; }
     const int pos = lower_bound_u64(skeys, 0, n_cap, (unsigned long long)c << 48);
-    out_offs[c] = rank[pos];
+    out_offs[c] = min(rank[pos], out_cap);      // clamped on overflow (status flag set by k_voxel_mean)
 }
 
 // ------------------------------------------------------------------------- cell list
@@ -155,10 +156,16 @@ k_ball_query(const float* __restrict__ q, const int32_t* __restrict__ q_offs, co
     const int slot = blockIdx.x * BQ_WARPS + warp;
     if (slot >= nq_cap) return;
     const int nq = q_offs[n_clouds];
-    if (slot >= nq) return;
-    const int qi = q_order ? q_order[slot] : slot;
-    if (qi < 0 || qi >= nq) return;           // q_order padded entries
     const int ns = s_offs[n_clouds];
+    const int qi = q_order ? q_order[slot] : slot;
+    if (qi < 0 || qi >= nq_cap) return;
+    if (qi >= nq) {                            // capacity padding: a fully-shadow row, so that the
+        for (int t = lane; t < K; t += 32) {   // whole (nq_cap, K) buffer is always initialised
+            if (out32) out32[(long long)qi * K + t] = ns;
+            if (out64) out64[(long long)qi * K + t] = ns;
+        }
+        return;
+    }
     const int c = regtr_cloud_of(q_offs, n_clouds, qi);
     const float qx = q[3 * qi + 0], qy = q[3 * qi + 1], qz = q[3 * qi + 2];
     const float cell = hdr->cell;
@@ -259,10 +266,10 @@ extern "C" {
 size_t regtr_grid_subsample_ws_bytes(int n_cap) { return n_cap > 0 ? carve(nullptr, n_cap).total : 256; }
 
 int regtr_grid_subsample(const float* xyz, const int32_t* offs, int n_clouds, int n_cap, float dl,
-                         float* out_xyz, int32_t* out_offs, uint32_t* status, void* ws, size_t ws_bytes,
-                         void* stream_) {
+                         float* out_xyz, int out_cap, int32_t* out_offs, uint32_t* status, void* ws,
+                         size_t ws_bytes, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
-    if (!offs || !out_offs || !status || n_clouds <= 0 || n_clouds > 32767 || n_cap < 0 || !(dl > 0.f))
+    if (!offs || !out_offs || !status || n_clouds <= 0 || n_clouds > 32767 || n_cap < 0 || out_cap < 0 || !(dl > 0.f))
         return REGTR_ERR_ARG;
     if (n_cap == 0) {
         cudaMemsetAsync(out_offs, 0, sizeof(int32_t) * (n_clouds + 1), st);
@@ -283,9 +290,11 @@ int regtr_grid_subsample(const float* xyz, const int32_t* offs, int n_clouds, in
     tb = w.cub_bytes;
     cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.vals_in, w.rank, n_cap + 1, st);
     REGTR_CHECK_LAUNCH();
-    k_voxel_mean<<<regtr_cdiv(n_cap, T), T, 0, st>>>(xyz, w.keys_out, w.vals_out, w.rank, n_cap, out_xyz);
+    k_voxel_mean<<<regtr_cdiv(n_cap, T), T, 0, st>>>(xyz, w.keys_out, w.vals_out, w.rank, n_cap, out_cap, out_xyz,
+                                                     status);
     REGTR_CHECK_LAUNCH();
-    k_cloud_offsets<<<regtr_cdiv(n_clouds + 1, 128), 128, 0, st>>>(w.keys_out, w.rank, n_cap, n_clouds, out_offs);
+    k_cloud_offsets<<<regtr_cdiv(n_clouds + 1, 128), 128, 0, st>>>(w.keys_out, w.rank, n_cap, n_clouds, out_cap,
+                                                                   out_offs);
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
 }

@@ -30,6 +30,41 @@ _CELL_SLACK = 1.0001   # cell = radius * slack: keeps |dx| < r inside the 27-cel
 
 # ------------------------------------------------------------------ pre-processing
 
+def level_capacities(cfg, cap0: int, ratio: float = 0.40, quantum: int = 256):
+    """Row capacities of every pyramid level for a static-shape (CUDA-graph) pipeline.
+    Each voxel-grid level keeps 19-27 % of the previous one on 3DMatch-like data (SURVEY.md 8:
+    38061 -> 10088 -> 2753 -> 751); `ratio` leaves ~50 % head-room and overflow is detected on the
+    device (REGTR_STATUS_CAPACITY), never silently wrong."""
+    levels, _, _ = pyramid_plan(cfg)
+    caps = [int(cap0)]
+    for _ in levels[1:]:
+        c = int(caps[-1] * ratio) + 1
+        caps.append(min(caps[-1], (c + quantum - 1) // quantum * quantum))
+    return caps
+
+
+class Pyramid:
+    """Device-resident KPConv pyramid with capacity-shaped buffers.  Level sizes live in
+    `offs_all[level]` (int32, device); nothing here requires a host synchronisation."""
+
+    def __init__(self, n_clouds, levels, caps, points, offs_all, conv32, conv64, pool32, pool64, up64, status):
+        self.n_clouds, self.levels, self.caps = n_clouds, levels, caps
+        self.points, self.offs_all = points, offs_all
+        self.conv32, self.conv64, self.pool32, self.pool64, self.up64 = conv32, conv64, pool32, pool64, up64
+        self.status = status
+
+    def n_dev(self, level):
+        """1-element int32 device view holding the number of points of `level`."""
+        return self.offs_all[level, self.n_clouds:]
+
+    def private(self, static=True):
+        """Private keys the encoder blocks consume (capacity tensors + device counts)."""
+        return dict(_points=self.points, _offs=[self.offs_all[l] for l in range(len(self.levels))],
+                    _neighbors32=self.conv32, _pools32=self.pool32,
+                    _ndev=[self.n_dev(l) for l in range(len(self.levels))] if static else None,
+                    _n_clouds=self.n_clouds)
+
+
 class PreprocessorGPU(nn.Module):
     """Computes the KPConv pyramid metadata on the GPU, deterministically.
 
@@ -38,9 +73,10 @@ class PreprocessorGPU(nn.Module):
     (int64 indices, shadow index = number of supports).  Differences by design:
       * bit-reproducible (sorted voxel order, index-ordered fp32 sums) where the reference
         is not (MinkowskiEngine hash order, Readme.md:99);
-      * one host synchronisation for the whole pyramid (level sizes), where the reference
-        synchronises at every `.item()` / python loop (kpconv.py:239,276-285).
-    Extra private keys (`_offs`, `_neighbors32`, `_pools32`, `_lens`) carry the int32 /
+      * ONE host synchronisation for the whole pyramid (`finalize`), where the reference
+        synchronises at every `.item()` / python loop (kpconv.py:239,276-285); `build` alone
+        is sync-free and CUDA-graph capturable.
+    Extra private keys (`_offs`, `_neighbors32`, `_pools32`, `_lens`, ...) carry the int32 /
     device-offset forms the encoder kernels consume.
     """
 
@@ -50,18 +86,17 @@ class PreprocessorGPU(nn.Module):
         self.compute_upsamples = compute_upsamples
 
     @torch.no_grad()
-    def forward(self, pts: List[torch.Tensor]):
-        cfg = self.cfg
-        levels, _, _ = pyramid_plan(cfg)
-        device = pts[0].device
-        n_clouds = len(pts)
-        lens0 = [int(p.shape[0]) for p in pts]
-        points = torch.cat([p.to(torch.float32) for p in pts], dim=0).contiguous()
-        cap = points.shape[0]
+    def build(self, points, offs0, n_clouds: int, caps=None, want64: bool = True) -> Pyramid:
+        """points (cap0,3) f32 packed clouds, offs0 (n_clouds+1) int32 device offsets.
+        caps: per-level row capacities (default: every level as large as level 0)."""
+        levels, _, _ = pyramid_plan(self.cfg)
+        device = points.device
+        cap0 = points.shape[0]
+        caps = [cap0] * len(levels) if caps is None else list(caps)
+        assert caps[0] == cap0
         status = ops.new_status(device)
         offs_all = torch.zeros((len(levels), n_clouds + 1), dtype=torch.int32, device=device)
-        offs_all[0].copy_(ops.make_offsets(lens0, device))
-
+        offs_all[0].copy_(offs0)
         pts_l, conv32, conv64, pool32, pool64, up64 = [], [], [], [], [], []
         cur = points
         grid = ops.CellGrid(cur, offs_all[0], n_clouds, levels[0]['radius'] * _CELL_SLACK, status)
@@ -70,64 +105,91 @@ class PreprocessorGPU(nn.Module):
             offs = offs_all[li]
             pts_l.append(cur)
             if lvl['has_conv']:
-                c32, c64 = ops.ball_query(cur, offs, cur, offs, grid, K, r, q_order=grid.order)
+                c32, c64 = ops.ball_query(cur, offs, cur, offs, grid, K, r, q_order=grid.order, want64=want64)
             else:
                 c32 = c64 = None
             conv32.append(c32); conv64.append(c64)
             if lvl['strided']:
-                nxt, _ = ops.grid_subsample(cur, offs, n_clouds, lvl['dl'], status, out_offs=offs_all[li + 1])
-                p32, p64 = ops.ball_query(nxt, offs_all[li + 1], cur, offs, grid, K, r)
+                nxt, _ = ops.grid_subsample(cur, offs, n_clouds, lvl['dl'], status, out_cap=caps[li + 1],
+                                            out_offs=offs_all[li + 1])
+                p32, p64 = ops.ball_query(nxt, offs_all[li + 1], cur, offs, grid, K, r, want64=want64)
                 nxt_grid = ops.CellGrid(nxt, offs_all[li + 1], n_clouds, 2 * r * _CELL_SLACK, status)
-                if self.compute_upsamples:
+                u64 = None
+                if self.compute_upsamples and want64:
                     _, u64 = ops.ball_query(cur, offs, nxt, offs_all[li + 1], nxt_grid, K, 2 * r,
                                             q_order=grid.order, want32=False)
-                else:
-                    u64 = None
                 pool32.append(p32); pool64.append(p64); up64.append(u64)
                 cur, grid = nxt, nxt_grid
             else:
                 pool32.append(None); pool64.append(None); up64.append(None)
+        return Pyramid(n_clouds, levels, caps, pts_l, offs_all, conv32, conv64, pool32, pool64, up64, status)
 
-        # ---- the single host synchronisation of the pyramid: level sizes + status word
-        host = torch.cat([offs_all.reshape(-1), status]).cpu()
-        if int(host[-1]) != 0:
+    @staticmethod
+    def check_status(code: int):
+        if code & 1:
             raise RuntimeError('point coordinates exceed the +-32766-cell key range of the voxel / cell grid')
-        offs_host = host[:-1].reshape(len(levels), n_clouds + 1)
+        if code & 2:
+            raise RuntimeError('a pyramid level overflowed its static capacity')
+
+    @staticmethod
+    def finalize(pyr: Pyramid, host=None):
+        """The single host synchronisation: read the level sizes, narrow the capacity buffers to
+        exact shapes and assemble the reference's dict.  `host` may carry an already-downloaded
+        (offs_all, status) pair."""
+        n_clouds, levels = pyr.n_clouds, pyr.levels
+        device = pyr.points[0].device
+        if host is None:
+            flat = torch.cat([pyr.offs_all.reshape(-1), pyr.status]).cpu()
+            offs_host, code = flat[:-1].reshape(len(levels), n_clouds + 1), int(flat[-1])
+        else:
+            offs_host, code = host
+        PreprocessorGPU.check_status(code)
         lens = [(offs_host[l, 1:] - offs_host[l, :-1]).tolist() for l in range(len(levels))]
         totals = [int(offs_host[l, -1]) for l in range(len(levels))]
-
         e_idx = torch.zeros((0, 1), dtype=torch.int64, device=device)
         data = dict(points=[], neighbors=[], pools=[], upsamples=[], stack_lengths=[],
-                    _offs=[], _neighbors32=[], _pools32=[], _lens=lens)
+                    _points=[], _offs=[], _neighbors32=[], _pools32=[], _lens=lens, _ndev=None,
+                    _n_clouds=n_clouds)
         for li, lvl in enumerate(levels):
             n = totals[li]
-            data['points'].append(pts_l[li][:n])
-            data['neighbors'].append(conv64[li][:n] if conv64[li] is not None else e_idx)
-            data['_neighbors32'].append(conv32[li][:n] if conv32[li] is not None else None)
+            data['points'].append(pyr.points[li][:n])
+            data['_points'].append(pyr.points[li][:n])
+            data['neighbors'].append(pyr.conv64[li][:n] if pyr.conv64[li] is not None else e_idx)
+            data['_neighbors32'].append(pyr.conv32[li][:n] if pyr.conv32[li] is not None else None)
             if lvl['strided']:
                 n2 = totals[li + 1]
-                data['pools'].append(pool64[li][:n2])
-                data['_pools32'].append(pool32[li][:n2])
-                data['upsamples'].append(up64[li][:n] if up64[li] is not None else e_idx)
+                data['pools'].append(pyr.pool64[li][:n2] if pyr.pool64[li] is not None else e_idx)
+                data['_pools32'].append(pyr.pool32[li][:n2])
+                data['upsamples'].append(pyr.up64[li][:n] if pyr.up64[li] is not None else e_idx)
             else:
                 data['pools'].append(e_idx)
                 data['_pools32'].append(None)
                 data['upsamples'].append(e_idx)
             data['stack_lengths'].append(torch.tensor(lens[li], dtype=torch.int64).to(device, non_blocking=True))
-            data['_offs'].append(offs_all[li])
+            data['_offs'].append(pyr.offs_all[li])
         return data
+
+    @torch.no_grad()
+    def forward(self, pts: List[torch.Tensor]):
+        device = pts[0].device
+        points = torch.cat([p.to(torch.float32) for p in pts], dim=0).contiguous()
+        offs0 = ops.make_offsets([int(p.shape[0]) for p in pts], device)
+        return self.finalize(self.build(points, offs0, len(pts)))
 
 
 def _meta_private(meta, device):
-    """int32 / offset forms of a pyramid dict; derived on the fly for a foreign (reference) dict."""
-    if '_offs' in meta:
-        return meta['_offs'], meta['_neighbors32'], meta['_pools32'], meta['_lens']
-    lens = [l.tolist() for l in meta['stack_lengths']]
-    offs = [ops.make_offsets(l, device) for l in lens]
-    n32 = [n.to(torch.int32).contiguous() if n.numel() and n.shape[1] > 1 else None for n in meta['neighbors']]
-    p32 = [p.to(torch.int32).contiguous() if p.numel() and p.shape[1] > 1 else None for p in meta['pools']]
-    meta.update(_offs=offs, _neighbors32=n32, _pools32=p32, _lens=lens)
-    return offs, n32, p32, lens
+    """Private (int32 / offsets) form of a pyramid dict; derived on the fly for a foreign
+    (reference-produced) dict."""
+    if '_offs' not in meta:
+        lens = [l.tolist() for l in meta['stack_lengths']]
+        meta.update(
+            _points=list(meta['points']), _offs=[ops.make_offsets(l, device) for l in lens],
+            _neighbors32=[n.to(torch.int32).contiguous() if n.numel() and n.shape[1] > 1 else None
+                          for n in meta['neighbors']],
+            _pools32=[p.to(torch.int32).contiguous() if p.numel() and p.shape[1] > 1 else None
+                      for p in meta['pools']],
+            _lens=lens, _ndev=None, _n_clouds=len(lens[0]))
+    return meta
 
 
 # --------------------------------------------------------------------------- blocks
@@ -160,10 +222,10 @@ class KPConv(nn.Module):
         self.kernel_points = nn.Parameter(torch.from_numpy(kernel_disposition(radius, kernel_size)),
                                           requires_grad=False)
 
-    def forward(self, q_pts, s_pts, neighb_inds, x):
+    def forward(self, q_pts, s_pts, neighb_inds, x, nq_dev=None, ns_dev=None):
         idx = neighb_inds if neighb_inds.dtype == torch.int32 else neighb_inds.to(torch.int32)
         return ops.kpconv(q_pts.contiguous(), s_pts.contiguous(), idx.contiguous(), x.contiguous(),
-                          self.weights, self.kernel_points, self.KP_extent)
+                          self.weights, self.kernel_points, self.KP_extent, nq_dev=nq_dev, ns_dev=ns_dev)
 
     def __repr__(self):
         return 'KPConv(radius: {:.2f}, extent: {:.2f}, in_feat: {:d}, out_feat: {:d})'.format(
@@ -212,11 +274,15 @@ class UnaryBlock(nn.Module):
 
 
 def _block_io(block, batch):
-    offs, n32, p32, _ = _meta_private(batch, batch['points'][0].device)
+    """-> (q_pts, s_pts, idx32, offs_pre, offs_post, nq_dev, ns_dev, n_clouds) for a block."""
+    m = _meta_private(batch, batch['points'][0].device if 'points' in batch else batch['_points'][0].device)
     li = block.layer_ind
+    pts, offs, nd = m['_points'], m['_offs'], m['_ndev']
     if 'strided' in block.block_name:
-        return (batch['points'][li + 1], batch['points'][li], p32[li], offs[li], offs[li + 1])
-    return (batch['points'][li], batch['points'][li], n32[li], offs[li], offs[li])
+        return (pts[li + 1], pts[li], m['_pools32'][li], offs[li], offs[li + 1],
+                nd[li + 1] if nd else None, nd[li] if nd else None, m['_n_clouds'])
+    return (pts[li], pts[li], m['_neighbors32'][li], offs[li], offs[li],
+            nd[li] if nd else None, nd[li] if nd else None, m['_n_clouds'])
 
 
 class SimpleBlock(nn.Module):
@@ -234,9 +300,9 @@ class SimpleBlock(nn.Module):
         self.batch_norm = BatchNormBlock(out_dim // 2, config.use_batch_norm, config.batch_norm_momentum)
 
     def forward(self, x, batch):
-        q, s, idx, _, offs_post = _block_io(self, batch)
-        y = self.KPConv(q, s, idx, x)
-        return self.batch_norm.fuse(y, offs_post, offs_post.numel() - 1, slope=0.1)
+        q, s, idx, _, offs_post, nq_dev, ns_dev, nc = _block_io(self, batch)
+        y = self.KPConv(q, s, idx, x, nq_dev, ns_dev)
+        return self.batch_norm.fuse(y, offs_post, nc, slope=0.1)
 
 
 class ResnetBottleneckBlock(nn.Module):
@@ -261,12 +327,11 @@ class ResnetBottleneckBlock(nn.Module):
             else nn.Identity()
 
     def forward(self, features, batch):
-        q, s, idx, offs_pre, offs_post = _block_io(self, batch)
-        nc = offs_pre.numel() - 1
+        q, s, idx, offs_pre, offs_post, nq_dev, ns_dev, nc = _block_io(self, batch)
         x = self.unary1.fuse(features, offs_pre, nc) if isinstance(self.unary1, UnaryBlock) else features
-        x = self.KPConv(q, s, idx, x)
+        x = self.KPConv(q, s, idx, x, nq_dev, ns_dev)
         x = self.batch_norm_conv.fuse(x, offs_post, nc, slope=0.1)
-        shortcut = ops.max_pool(features, idx) if 'strided' in self.block_name else features
+        shortcut = ops.max_pool(features, idx, ns_dev) if 'strided' in self.block_name else features
         if isinstance(self.unary_shortcut, UnaryBlock):
             shortcut = self.unary_shortcut.fuse(shortcut, offs_post, nc)
         # LeakyReLU(unary2(x) + shortcut), fused into unary2's normalisation pass

@@ -32,19 +32,20 @@ SIGNATURES = {
     'regtr_version': (_I, []),
     'regtr_build_info': (_c.c_char_p, []),
     'regtr_grid_subsample_ws_bytes': (_Z, [_I]),
-    'regtr_grid_subsample': (_I, [_P, _P, _I, _I, _F, _P, _P, _P, _P, _Z, _P]),
+    'regtr_grid_subsample': (_I, [_P, _P, _I, _I, _F, _P, _I, _P, _P, _P, _Z, _P]),
     'regtr_cellgrid_bytes': (_Z, [_I]),
     'regtr_cellgrid_ws_bytes': (_Z, [_I]),
     'regtr_cellgrid_build': (_I, [_P, _P, _I, _I, _F, _P, _P, _P, _P, _Z, _P]),
     'regtr_ball_query': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
     'regtr_kpconv_ws_bytes': (_Z, [_I, _I, _I]),
-    'regtr_kpconv_fwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _Z, _P]),
-    'regtr_kpconv_aggregate': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
-    'regtr_max_pool': (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    'regtr_kpconv_fwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _F, _P, _P, _Z, _P]),
+    'regtr_kpconv_aggregate': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _F, _P, _P, _P]),
+    'regtr_max_pool': (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _P]),
     'regtr_instnorm_ws_bytes': (_Z, [_I, _I, _I]),
     'regtr_instnorm_act': (_I, [_P, _P, _I, _I, _I, _F, _P, _F, _P, _P, _Z, _P]),
     'regtr_pos_embed_sine': (_I, [_P, _I, _P, _I, _I, _F, _P, _P]),
     'regtr_layernorm_pos': (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P]),
+    'regtr_attention_plan': (_I, [_P, _I, _P, _P]),
     'regtr_mha_varlen_fwd': (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     'regtr_kabsch_fwd': (_I, [_P, _P, _P, _P, _I, _P, _P]),
     'regtr_pose_from_corr': (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),

@@ -72,17 +72,21 @@ def new_status(device) -> torch.Tensor:
 
 # ---------------------------------------------------------------- pre-processing
 
-def grid_subsample(xyz, offs, n_clouds: int, dl: float, status, out_xyz=None, out_offs=None):
-    """-> (out_xyz (n_cap,3) capacity buffer, out_offs (n_clouds+1) int32).  No host sync."""
+def grid_subsample(xyz, offs, n_clouds: int, dl: float, status, out_cap=None, out_offs=None):
+    """-> (out_xyz (out_cap,3) capacity buffer, out_offs (n_clouds+1) int32).  No host sync.
+    out_cap defaults to the input capacity (always sufficient); a smaller value is memory-safe but
+    raises REGTR_STATUS_CAPACITY in `status` when the sub-sampled level does not fit."""
     L = _lib.load()
     _chk(xyz, torch.float32, 'xyz', 2); _chk(offs, torch.int32, 'offs', 1)
     n_cap = xyz.shape[0]
-    out_xyz = torch.empty_like(xyz) if out_xyz is None else out_xyz
+    out_cap = n_cap if out_cap is None else int(out_cap)
+    out_xyz = torch.empty((out_cap, 3), dtype=torch.float32, device=xyz.device)
     out_offs = torch.empty(n_clouds + 1, dtype=torch.int32, device=xyz.device) if out_offs is None else out_offs
     nb = L.regtr_grid_subsample_ws_bytes(n_cap)
     ws = workspace(nb, xyz.device)
-    _lib.check(L.regtr_grid_subsample(_p(xyz), _p(offs), n_clouds, n_cap, float(dl), _p(out_xyz), _p(out_offs),
-                                      _p(status), _p(ws), ws.numel(), _stream()), 'regtr_grid_subsample')
+    _lib.check(L.regtr_grid_subsample(_p(xyz), _p(offs), n_clouds, n_cap, float(dl), _p(out_xyz), out_cap,
+                                      _p(out_offs), _p(status), _p(ws), ws.numel(), _stream()),
+               'regtr_grid_subsample')
     _count(4)
     return out_xyz, out_offs
 
@@ -126,8 +130,10 @@ def ball_query(q, q_offs, s, s_offs, grid: CellGrid, K: int, radius: float, q_or
 
 # ------------------------------------------------------------------------ encoder
 
-def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=None):
-    """KPConv.forward (rigid / linear / sum).  idx32 (Nq,K) int32, x (Ns,Cin) -> (Nq,Cout)."""
+def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=None, nq_dev=None, ns_dev=None):
+    """KPConv.forward (rigid / linear / sum).  idx32 (Nq,K) int32, x (Ns,Cin) -> (Nq,Cout).
+    nq_dev / ns_dev: optional 1-element int32 device tensors with the actual counts when the
+    leading dimensions are capacities."""
     L = _lib.load()
     _chk(q_pts, torch.float32, 'q_pts', 2); _chk(s_pts, torch.float32, 's_pts', 2)
     _chk(idx32, torch.int32, 'neighb_inds', 2); _chk(x, torch.float32, 'x', 2)
@@ -144,9 +150,9 @@ def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=No
     if trace is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _lib.check(L.regtr_kpconv_fwd(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(weights), _p(kernel_points), Nq, Ns, K,
-                                  Cin, Cout, float(extent), _p(out), _p(ws), ws.numel(), _stream()),
-               'regtr_kpconv_fwd')
+    _lib.check(L.regtr_kpconv_fwd(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(weights), _p(kernel_points), Nq, Ns,
+                                  _p(nq_dev), _p(ns_dev), K, Cin, Cout, float(extent), _p(out), _p(ws), ws.numel(),
+                                  _stream()), 'regtr_kpconv_fwd')
     if trace is not None:
         e1.record()
         trace.append((e0, e1, dict(Nq=Nq, Ns=Ns, K=K, Cin=Cin, Cout=Cout, idx=idx32)))
@@ -154,25 +160,26 @@ def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=No
     return out
 
 
-def kpconv_aggregate(q_pts, s_pts, idx32, x, kernel_points, extent: float, wf=None):
+def kpconv_aggregate(q_pts, s_pts, idx32, x, kernel_points, extent: float, wf=None, nq_dev=None, ns_dev=None):
     """Gather + influence + aggregation only: -> wf (Nq, 15*Cin) (already / neighbour count)."""
     L = _lib.load()
     Nq, K = idx32.shape
     Ns, Cin = x.shape
     wf = torch.empty((Nq, 15 * Cin), dtype=torch.float32, device=x.device) if wf is None else wf
     flags = workspace(max(Ns, 1), x.device, 'rowflags')
-    _lib.check(L.regtr_kpconv_aggregate(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(kernel_points), Nq, Ns, K, Cin,
-                                        float(extent), _p(wf), _p(flags), _stream()), 'regtr_kpconv_aggregate')
+    _lib.check(L.regtr_kpconv_aggregate(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(kernel_points), Nq, Ns,
+                                        _p(nq_dev), _p(ns_dev), K, Cin, float(extent), _p(wf), _p(flags), _stream()),
+               'regtr_kpconv_aggregate')
     _count(2)
     return wf
 
 
-def max_pool(x, idx32):
+def max_pool(x, idx32, ns_dev=None):
     L = _lib.load()
     _chk(x, torch.float32, 'x', 2); _chk(idx32, torch.int32, 'inds', 2)
     Nq, K = idx32.shape
     out = torch.empty((Nq, x.shape[1]), dtype=torch.float32, device=x.device)
-    _lib.check(L.regtr_max_pool(_p(x), _p(idx32), Nq, x.shape[0], K, x.shape[1], _p(out), _stream()),
+    _lib.check(L.regtr_max_pool(_p(x), _p(idx32), Nq, x.shape[0], _p(ns_dev), K, x.shape[1], _p(out), _stream()),
                'regtr_max_pool')
     _count(1)
     return out
@@ -238,6 +245,16 @@ def layernorm_pos(x, gamma, beta, pos=None, eps: float = 1e-5, want_plain=True, 
     return y, yp
 
 
+def attention_plan(offs, B: int):
+    """Device-side (4, 2B) int32 table: q_start, q_len, cross k_start, cross k_len.  No host sync."""
+    L = _lib.load()
+    _chk(offs, torch.int32, 'offs', 1)
+    plan = torch.empty((4, 2 * B), dtype=torch.int32, device=offs.device)
+    _lib.check(L.regtr_attention_plan(_p(offs), B, _p(plan), _stream()), 'regtr_attention_plan')
+    _count(1)
+    return plan
+
+
 def mha_varlen(q, k, v, q_start, q_len, k_start, k_len, max_q_len: int, n_heads: int, out=None):
     """softmax(q k^T / sqrt(dh)) v per head over explicit (query range, key range) problems.
     q/k/v may be column slices of a wider row-major matrix (stride(0) is the leading dim)."""
@@ -247,7 +264,8 @@ def mha_varlen(q, k, v, q_start, q_len, k_start, k_len, max_q_len: int, n_heads:
             raise ValueError(f'mha_varlen: {nm} must be a CUDA fp32 matrix with unit column stride')
     E = q.shape[1]
     dh = E // n_heads
-    out = torch.empty((q.shape[0], E), dtype=torch.float32, device=q.device) if out is None else out
+    # zeros: rows outside every problem (capacity padding) stay finite for the GEMMs downstream
+    out = torch.zeros((q.shape[0], E), dtype=torch.float32, device=q.device) if out is None else out
     _lib.check(L.regtr_mha_varlen_fwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
                                       out.stride(0), _p(q_start), _p(q_len), _p(k_start), _p(k_len),
                                       q_start.numel(), int(max_q_len), n_heads, dh, 1.0 / math.sqrt(dh), _stream()),

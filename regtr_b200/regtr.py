@@ -83,38 +83,147 @@ class RegTR(nn.Module):
     def device(self):
         return next(self.parameters()).device
 
-    @torch.no_grad()
-    def forward(self, batch):
+    # ------------------------------------------------------------------ core (sync-free)
+    def _core(self, meta, B: int, plan: AttentionPlan):
+        """Encoder -> projection -> position embedding -> cross-encoder -> regressor -> pose on
+        packed (possibly capacity-padded) rows.  No host synchronisation, CUDA-graph capturable."""
         cfg = self.cfg
-        B = len(batch['src_xyz'])
-        # pyramid (regtr.py:117-122); a single host sync inside
-        meta = self.preprocessor(list(batch['src_xyz']) + list(batch['tgt_xyz']))
-        batch['kpconv_meta'] = meta
-        lens_c = meta['_lens'][-1]
-        feats0 = torch.ones_like(meta['points'][0][:, 0:1])
-        # KPConv encoder -> bottleneck projection (regtr.py:136-146)
-        feats_un, _ = self.kpf_encoder(feats0, meta)
-        both_un = self.feat_proj(feats_un)
-        # positions of the coarsest level and their embedding (regtr.py:149-154)
-        xyz_c = meta['points'][-1]
-        pe = self.pos_embed(xyz_c)
-        # cross-encoder on packed tokens (regtr.py:156-166)
-        plan = AttentionPlan(lens_c, xyz_c.device)
+        pts = meta['_points']
+        feats0 = torch.ones_like(pts[0][:, 0:1])                                   # regtr.py:122
+        feats_un, _ = self.kpf_encoder(feats0, meta)                               # regtr.py:136
+        both_un = self.feat_proj(feats_un)                                         # regtr.py:145
+        xyz_c = pts[-1]
+        pe = self.pos_embed(xyz_c)                                                 # regtr.py:149-154
         cond = self.transformer_encoder.forward_packed(
             both_un.contiguous(), pe if cfg.transformer_encoder_has_pos_emb else None, plan)   # (L,N,E)
-        # correspondence regression on all layers (regtr.py:168-171)
-        corr, logit = self.correspondence_decoder.forward_packed(cond)                        # (L,N,3), (L,N,1)
+        corr, logit = self.correspondence_decoder.forward_packed(cond)             # regtr.py:168-171
         # correspondences + sigmoid + weighted Kabsch, one launch (regtr.py:185-203)
         pose = ops.pose_from_corr(xyz_c, corr.contiguous(), logit[..., 0].contiguous(), meta['_offs'][-1], B)
+        return dict(both_un=both_un, xyz_c=xyz_c, cond=cond, corr=corr, logit=logit, pose=pose)
 
-        split = lambda t, dim=0: torch.split(t, lens_c, dim=dim)
-        un, kp = split(both_un), split(xyz_c)
-        feat, warped, ovl = split(cond, 1), split(corr, 1), split(logit, 1)
+    @staticmethod
+    def _assemble(core, lens_c, B):
+        """Per-cloud views in the reference's output layout (regtr.py:218-234)."""
+        n = sum(lens_c)
+        split = lambda t, dim=0: torch.split(t.narrow(dim, 0, n), lens_c, dim=dim)
+        un, kp = split(core['both_un']), split(core['xyz_c'])
+        feat, warped, ovl = split(core['cond'], 1), split(core['corr'], 1), split(core['logit'], 1)
         return {
             'src_feat_un': un[:B], 'tgt_feat_un': un[B:],
             'src_feat': list(feat[:B]), 'tgt_feat': list(feat[B:]),
             'src_kp': kp[:B], 'src_kp_warped': list(warped[:B]),
             'tgt_kp': kp[B:], 'tgt_kp_warped': list(warped[B:]),
             'src_overlap': list(ovl[:B]), 'tgt_overlap': list(ovl[B:]),
-            'pose': pose,
+            'pose': core['pose'],
         }
+
+    @torch.no_grad()
+    def forward(self, batch):
+        """Eager path: exact shapes, one host sync (pyramid sizes) before the encoder."""
+        B = len(batch['src_xyz'])
+        meta = self.preprocessor(list(batch['src_xyz']) + list(batch['tgt_xyz']))    # regtr.py:117-118
+        batch['kpconv_meta'] = meta
+        lens_c = meta['_lens'][-1]
+        plan = AttentionPlan(lens_c, meta['_points'][-1].device)
+        return self._assemble(self._core(meta, B, plan), lens_c, B)
+
+
+class GraphedRegTR:
+    """CUDA-graph executor of `RegTR.forward` for latency-bound serving (batch 1..B pairs).
+
+    The eager forward is launch-bound: ~370 kernels of a few microseconds each.
+    Here the whole forward -- pyramid, encoder, cross-encoder, regressor, Kabsch -- is captured
+    ONCE per (pairs, level-0 capacity bucket) into a CUDA graph over capacity-shaped buffers;
+    data-dependent level sizes stay on the device (int32 offsets read by every kernel), so a
+    replay needs no host round trip.  Per call: one packed H2D/D2D copy of the points, one graph
+    launch, one small D2H (level sizes + status + pose) and a single synchronisation.
+
+    Outputs are views into the graph's static buffers: valid until the next call with the same
+    bucket.  If a level overflows its static capacity (REGTR_STATUS_CAPACITY) the call falls back
+    to the eager forward, so results are never silently truncated.
+    """
+
+    def __init__(self, model: RegTR, bucket: int = 8192, full_meta: bool = True):
+        self.model = model
+        self.bucket = int(bucket)
+        self.full_meta = full_meta
+        self.graphs = {}
+        self.fallbacks = 0
+
+    def _capture(self, B: int, cap0: int):
+        from .kpconv import level_capacities
+        model = self.model
+        dev = model.device
+        caps = level_capacities(model.cfg, cap0)
+        st = dict(points=torch.zeros((cap0, 3), dtype=torch.float32, device=dev),
+                  offs0=torch.zeros(2 * B + 1, dtype=torch.int32, device=dev), caps=caps)
+
+        def run():
+            pyr = model.preprocessor.build(st['points'], st['offs0'], 2 * B, caps=caps, want64=self.full_meta)
+            plan = AttentionPlan.from_device(pyr.offs_all[-1], B, caps[-1])
+            core = model._core(pyr.private(static=True), B, plan)
+            tail = torch.cat([pyr.offs_all.reshape(-1), pyr.status])
+            return pyr, core, tail
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):           # warm-up (sizes workspaces, cuBLAS, caches) before capture
+            # a plausible offset table so that the warm-up exercises every kernel
+            n = cap0 // (2 * B)
+            st['offs0'].copy_(torch.arange(0, 2 * B + 1, dtype=torch.int32, device=dev) * n)
+            st['points'].uniform_(-1.0, 1.0)
+            for _ in range(2):
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            pyr, core, tail = run()
+        st.update(graph=g, pyr=pyr, core=core, tail=tail,
+                  tail_host=torch.empty(tail.numel(), dtype=torch.int32).pin_memory(),
+                  pose_host=torch.empty(tuple(core['pose'].shape), dtype=torch.float32).pin_memory(),
+                  stage=torch.empty((cap0, 3), dtype=torch.float32).pin_memory())
+        return st
+
+    @torch.no_grad()
+    def __call__(self, batch):
+        model = self.model
+        dev = model.device
+        src, tgt = list(batch['src_xyz']), list(batch['tgt_xyz'])
+        B = len(src)
+        clouds = src + tgt
+        lens0 = [int(c.shape[0]) for c in clouds]
+        n0 = sum(lens0)
+        cap0 = max(self.bucket, (n0 + self.bucket - 1) // self.bucket * self.bucket)
+        key = (B, cap0)
+        st = self.graphs.get(key)
+        if st is None:
+            st = self.graphs[key] = self._capture(B, cap0)
+        # ---- inputs -> static buffers (one packed copy)
+        offs = [0]
+        for v in lens0:
+            offs.append(offs[-1] + v)
+        if clouds[0].is_cuda:
+            torch.cat(clouds, dim=0, out=st['points'][:n0])
+        else:                                   # host clouds: pack into pinned staging, one H2D
+            torch.cat(clouds, dim=0, out=st['stage'][:n0])
+            st['points'][:n0].copy_(st['stage'][:n0], non_blocking=True)
+        st['offs0'].copy_(torch.tensor(offs, dtype=torch.int32), non_blocking=True)
+        # ---- replay + the single D2H / sync
+        st['graph'].replay()
+        st['tail_host'].copy_(st['tail'], non_blocking=True)
+        st['pose_host'].copy_(st['core']['pose'], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        pyr = st['pyr']
+        n_lvl = len(pyr.levels)
+        host = st['tail_host']
+        code = int(host[-1])
+        if code & 2:                            # a level overflowed its capacity: redo eagerly
+            self.fallbacks += 1
+            return model.forward(batch)
+        offs_host = host[:-1].reshape(n_lvl, 2 * B + 1)
+        meta = model.preprocessor.finalize(pyr, host=(offs_host, code))
+        batch['kpconv_meta'] = meta
+        out = model._assemble(st['core'], meta['_lens'][-1], B)
+        out['pose_host'] = st['pose_host']
+        return out

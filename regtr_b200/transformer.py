@@ -56,21 +56,29 @@ class _MHAParams(nn.Module):
 
 
 class AttentionPlan:
-    """Device-side (start,len) tables of the self and cross attention problems of a batch."""
+    """Device-side (start,len) tables of the self and cross attention problems of a batch:
+    problem c = cloud c of the (src x B, tgt x B) stack; its cross partner is the other cloud of
+    the pair.  `max_len` is a host-side upper bound of the sequence lengths (grid sizing only)."""
 
-    def __init__(self, lens, device):
-        n2 = len(lens)
-        B = n2 // 2
-        starts = [0]
-        for v in lens:
-            starts.append(starts[-1] + int(v))
-        other = [B + c if c < B else c - B for c in range(n2)]
-        rows = [starts[:n2], list(map(int, lens)),                      # query ranges (self and cross)
-                [starts[o] for o in other], [int(lens[o]) for o in other]]  # cross key ranges
-        t = torch.tensor(rows, dtype=torch.int32).to(device)
-        self.q_start, self.q_len, self.xk_start, self.xk_len = t[0], t[1], t[2], t[3]
-        self.max_len = max(map(int, lens)) if n2 else 0
-        self.n_tokens = starts[-1]
+    def __init__(self, lens=None, device=None, table=None, max_len=None):
+        if table is None:
+            n2 = len(lens)
+            B = n2 // 2
+            starts = [0]
+            for v in lens:
+                starts.append(starts[-1] + int(v))
+            other = [B + c if c < B else c - B for c in range(n2)]
+            rows = [starts[:n2], list(map(int, lens)),                          # query ranges
+                    [starts[o] for o in other], [int(lens[o]) for o in other]]  # cross key ranges
+            table = torch.tensor(rows, dtype=torch.int32).to(device)
+            max_len = max(map(int, lens)) if n2 else 0
+        self.q_start, self.q_len, self.xk_start, self.xk_len = table[0], table[1], table[2], table[3]
+        self.max_len = int(max_len)
+
+    @classmethod
+    def from_device(cls, offs, B: int, max_len: int):
+        """Sync-free construction from device offsets (static-shape / CUDA-graph pipelines)."""
+        return cls(table=ops.attention_plan(offs, B), max_len=max_len)
 
 
 class TransformerCrossEncoderLayer(nn.Module):

@@ -260,3 +260,43 @@ def test_forward_is_deterministic_and_batch_invariant():
     assert torch.equal(o1['pose'], o1b['pose'])
     assert torch.equal(o1['src_kp'][0], o3['src_kp'][1])
     assert float((o1['pose'][:, 0] - o3['pose'][:, 1]).abs().max()) <= 2e-5
+
+
+def test_graphed_executor_matches_eager_and_survives_overflow():
+    """CUDA-graph executor (static capacities, device-side sizes) vs the eager forward: identical
+    indices / key points, near-identical floats; several inputs through ONE captured graph; host
+    (pinned) inputs; and the eager fallback when a level overflows its static capacity."""
+    from regtr_b200.config import get_config
+    from regtr_b200.regtr import GraphedRegTR, RegTR
+    from regtr_b200.synthetic import make_3dmatch_pair
+    from regtr_b200.weights import random_state_dict
+    cfg = get_config('3dmatch')
+    sd = random_state_dict(cfg, 8)
+    model = RegTR(cfg).to(DEV).eval()
+    model.load_state_dict(sd, strict=True)
+    runner = GraphedRegTR(model, bucket=16384)
+    for i, n in enumerate((5000, 6000, 5500)):
+        p = make_3dmatch_pair(2200 + i, n)
+        b_e = {'src_xyz': [G(p['src_xyz'])], 'tgt_xyz': [G(p['tgt_xyz'])]}
+        b_g = {'src_xyz': [G(p['src_xyz'])], 'tgt_xyz': [G(p['tgt_xyz'])]} if i != 1 else \
+            {'src_xyz': [torch.from_numpy(p['src_xyz']).pin_memory()], 'tgt_xyz': [torch.from_numpy(p['tgt_xyz']).pin_memory()]}
+        want = model(b_e)
+        got = runner(b_g)
+        for key in ('neighbors', 'pools', 'upsamples', 'points', 'stack_lengths'):
+            for a, b in zip(b_g['kpconv_meta'][key], b_e['kpconv_meta'][key]):
+                assert torch.equal(a, b), key
+        assert torch.equal(got['src_kp'][0], want['src_kp'][0])
+        s = float(want['src_feat'][0].abs().max())
+        assert float((got['src_feat'][0] - want['src_feat'][0]).abs().max()) <= 2e-5 * s
+        assert float((got['pose'] - want['pose']).abs().max()) <= 2e-5
+        assert torch.equal(got['pose_host'], got['pose'].cpu())
+    assert len(runner.graphs) == 1 and runner.fallbacks == 0
+    # volume-filling cloud: every point its own voxel -> level 1 does not fit 0.4 * cap0 -> eager fallback
+    rng = np.random.default_rng(0)
+    src = rng.uniform(-2, 2, size=(7000, 3)).astype(np.float32)
+    tgt = rng.uniform(-2, 2, size=(7000, 3)).astype(np.float32)
+    b_e = {'src_xyz': [G(src)], 'tgt_xyz': [G(tgt)]}
+    b_g = {'src_xyz': [G(src)], 'tgt_xyz': [G(tgt)]}
+    want, got = model(b_e), runner(b_g)
+    assert runner.fallbacks == 1
+    assert torch.equal(got['pose'], want['pose'])
