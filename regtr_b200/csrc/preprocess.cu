@@ -244,7 +244,7 @@ SubWs carve(void* ws, int n_cap) {
     auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += regtr_align(bytes); return (void*)r; };
     w.keys_in = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)n_cap);
     w.keys_out = (unsigned long long*)take(sizeof(unsigned long long) * (size_t)n_cap);
-    w.vals_in = (int32_t*)take(sizeof(int32_t) * (size_t)n_cap);
+    w.vals_in = (int32_t*)take(sizeof(int32_t) * ((size_t)n_cap + 1));   // also holds the n_cap+1 head flags
     w.vals_out = (int32_t*)take(sizeof(int32_t) * (size_t)n_cap);
     w.rank = (int32_t*)take(sizeof(int32_t) * ((size_t)n_cap + 1));
     w.cub_bytes = cub_tmp_bytes(n_cap);
