@@ -122,6 +122,26 @@ int regtr_instnorm_act(const float* x, const int32_t* offs, int n_clouds, int n_
                        const float* res, float slope, float* out, void* ws, size_t ws_bytes,
                        void* stream);
 
+/* ---- dense layers ---------------------------------------------------------------- */
+
+/* x = hi + lo with both halves exactly representable in TF32 (low 13 mantissa bits zero);
+ * used to pre-split weight matrices for regtr_gemm_tf32x3. */
+int regtr_split_tf32(const float* x, long long n, float* hi, float* lo, void* stream);
+
+/* fp32-accurate GEMM on the tcgen05 tensor cores (3xTF32):
+ *   C[M,N] = act(A[M,K] @ B[N,K]^T + bias[N] + R[M,N]),  B given pre-split as B_hi / B_lo.
+ * Replaces nn.Linear (kpconv_blocks.py:546, regtr.py:36/145, transformers.py:95-101,
+ * regtr.py:404-411) and the KPConv weight contraction (kpconv_blocks.py:401-406).
+ * Row-major fp32; lda/ldb multiples of 4 and 16-byte aligned bases (TMA); bias / R optional;
+ * m_dev (optional device int32): actual row count when M is a capacity; relu != 0 applies ReLU.
+ * ws: regtr_gemm_ws_bytes(M,N,K) bytes (deterministic split-K planes for skinny long-K shapes;
+ * also limits the tensor cores' truncating fp32 accumulation to short K runs). */
+size_t regtr_gemm_ws_bytes(int M, int N, int K);
+int regtr_gemm_tf32x3(const float* A, int lda, const float* B_hi, const float* B_lo, int ldb,
+                      float* C, int ldc, const float* bias, const float* R, int ldr,
+                      int M, int N, int K, const int32_t* m_dev, int relu,
+                      void* ws, size_t ws_bytes, void* stream);
+
 /* ---- transformer ------------------------------------------------------------------ */
 
 /* 3-D sine position embedding.  Replaces PositionEmbeddingCoordsSine.forward

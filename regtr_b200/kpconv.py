@@ -264,9 +264,10 @@ class UnaryBlock(nn.Module):
         self.mlp = nn.Linear(in_dim, out_dim, bias=False)
         self.batch_norm = BatchNormBlock(out_dim, use_bn, bn_momentum)
 
-    def fuse(self, x, offs, n_clouds, res=None, final_slope=None):
+    def fuse(self, x, offs, n_clouds, res=None, final_slope=None, m_dev=None):
         slope = final_slope if final_slope is not None else (-1.0 if self.no_relu else 0.1)
-        return self.batch_norm.fuse(F.linear(x, self.mlp.weight), offs, n_clouds, res=res, slope=slope)
+        return self.batch_norm.fuse(ops.linear(x, self.mlp.weight, m_dev=m_dev), offs, n_clouds, res=res,
+                                    slope=slope)
 
     def forward(self, x, stack_lengths=None):
         offs = ops.make_offsets(stack_lengths, x.device)
@@ -328,14 +329,15 @@ class ResnetBottleneckBlock(nn.Module):
 
     def forward(self, features, batch):
         q, s, idx, offs_pre, offs_post, nq_dev, ns_dev, nc = _block_io(self, batch)
-        x = self.unary1.fuse(features, offs_pre, nc) if isinstance(self.unary1, UnaryBlock) else features
+        x = self.unary1.fuse(features, offs_pre, nc, m_dev=ns_dev) if isinstance(self.unary1, UnaryBlock) \
+            else features
         x = self.KPConv(q, s, idx, x, nq_dev, ns_dev)
         x = self.batch_norm_conv.fuse(x, offs_post, nc, slope=0.1)
         shortcut = ops.max_pool(features, idx, ns_dev) if 'strided' in self.block_name else features
         if isinstance(self.unary_shortcut, UnaryBlock):
-            shortcut = self.unary_shortcut.fuse(shortcut, offs_post, nc)
+            shortcut = self.unary_shortcut.fuse(shortcut, offs_post, nc, m_dev=nq_dev)
         # LeakyReLU(unary2(x) + shortcut), fused into unary2's normalisation pass
-        return self.unary2.fuse(x, offs_post, nc, res=shortcut, final_slope=0.1)
+        return self.unary2.fuse(x, offs_post, nc, res=shortcut, final_slope=0.1, m_dev=nq_dev)
 
 
 def block_decider(block_name, radius, in_dim, out_dim, layer_ind, config):

@@ -56,6 +56,10 @@ def workspace(nbytes: int, device, slot: str = 'default') -> torch.Tensor:
     return buf
 
 
+def regtr_align_up(n, a=256):
+    return (n + a - 1) // a * a
+
+
 def make_offsets(lengths, device) -> torch.Tensor:
     """int32 prefix offsets (n_clouds+1) on `device` from a host list / tensor of lengths."""
     if torch.is_tensor(lengths):
@@ -150,13 +154,24 @@ def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=No
     if trace is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    _lib.check(L.regtr_kpconv_fwd(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(weights), _p(kernel_points), Nq, Ns,
-                                  _p(nq_dev), _p(ns_dev), K, Cin, Cout, float(extent), _p(out), _p(ws), ws.numel(),
-                                  _stream()), 'regtr_kpconv_fwd')
+    if GEMM_BACKEND == 'tc3x' and (15 * Cin) % 4 == 0:
+        # gather/aggregate kernel, then the [Nq,15Cin] x [15Cin,Cout] contraction on the tensor cores
+        wf = ws[:Nq * 15 * Cin * 4].view(torch.float32).view(Nq, 15 * Cin)
+        flags = ws[regtr_align_up(Nq * 15 * Cin * 4):]
+        _lib.check(L.regtr_kpconv_aggregate(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(kernel_points), Nq, Ns,
+                                            _p(nq_dev), _p(ns_dev), K, Cin, float(extent), _p(wf), _p(flags),
+                                            _stream()), 'regtr_kpconv_aggregate')
+        _count(2)
+        hi, lo = split_weight(weights.view(15 * Cin, Cout), transpose=True)
+        gemm(wf, hi, lo, m_dev=nq_dev, out=out)
+    else:
+        _lib.check(L.regtr_kpconv_fwd(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(weights), _p(kernel_points), Nq, Ns,
+                                      _p(nq_dev), _p(ns_dev), K, Cin, Cout, float(extent), _p(out), _p(ws),
+                                      ws.numel(), _stream()), 'regtr_kpconv_fwd')
+        _count(2)
     if trace is not None:
         e1.record()
         trace.append((e0, e1, dict(Nq=Nq, Ns=Ns, K=K, Cin=Cin, Cout=Cout, idx=idx32)))
-    _count(2)
     return out
 
 
@@ -199,6 +214,64 @@ def instnorm_act(x, offs, n_clouds: int, res=None, slope: float = -1.0, eps: flo
                                     _p(ws), ws.numel(), _stream()), 'regtr_instnorm_act')
     _count(2)
     return out
+
+
+# -------------------------------------------------------------------- dense layers
+
+_split_cache = {}
+
+
+def split_weight(w: torch.Tensor, transpose: bool = False):
+    """(hi, lo) TF32 halves of a weight matrix [N,K] (or of its transpose), cached per parameter
+    storage + version so that inference pays the split once."""
+    L = _lib.load()
+    key = (w.data_ptr(), w._version, tuple(w.shape), transpose)
+    hit = _split_cache.get(key)
+    if hit is not None:
+        return hit
+    src = (w.detach().t() if transpose else w.detach()).contiguous().to(torch.float32)
+    hi, lo = torch.empty_like(src), torch.empty_like(src)
+    _lib.check(L.regtr_split_tf32(_p(src), src.numel(), _p(hi), _p(lo), _stream()), 'regtr_split_tf32')
+    _count(1)
+    if len(_split_cache) > 4096:
+        _split_cache.clear()
+    _split_cache[key] = (hi, lo)
+    return hi, lo
+
+
+def gemm(a, b_hi, b_lo, bias=None, residual=None, relu=False, m_dev=None, out=None):
+    """act(a @ B^T + bias + residual) with B = b_hi + b_lo ([N,K] row-major), 3xTF32 tcgen05 kernel."""
+    L = _lib.load()
+    if not a.is_cuda or a.dtype != torch.float32 or a.dim() != 2 or a.stride(1) != 1:
+        raise ValueError('gemm: A must be a CUDA fp32 matrix with unit column stride')
+    M, K = a.shape
+    N = b_hi.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device) if out is None else out
+    nb = L.regtr_gemm_ws_bytes(M, N, K)
+    ws = workspace(nb, a.device, 'gemm')
+    _lib.check(L.regtr_gemm_tf32x3(_p(a), a.stride(0), _p(b_hi), _p(b_lo), b_hi.stride(0), _p(out), out.stride(0),
+                                   _p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
+                                   M, N, K, _p(m_dev), 1 if relu else 0, _p(ws), ws.numel(), _stream()),
+               'regtr_gemm_tf32x3')
+    _count(2 if nb > 256 else 1)
+    return out
+
+
+# 'tc3x': hand-written tcgen05 3xTF32 GEMM (default);  'cublas': torch / cuBLAS fp32 SIMT sgemm
+GEMM_BACKEND = 'tc3x'
+
+
+def linear(x, weight, bias=None, residual=None, relu=False, m_dev=None):
+    """nn.Linear forward (x @ weight^T + bias) (+ residual, + ReLU).
+    Default: the 3xTF32 tcgen05 GEMM of this library (needs K % 4 == 0 for the TMA row pitch);
+    `GEMM_BACKEND = 'cublas'` or an unsupported K routes to cuBLAS as a plain library GEMM."""
+    if GEMM_BACKEND == 'tc3x' and x.shape[1] % 4 == 0 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0:
+        hi, lo = split_weight(weight)
+        return gemm(x, hi, lo, bias=bias, residual=residual, relu=relu, m_dev=m_dev)
+    y = torch.nn.functional.linear(x, weight, bias)
+    if residual is not None:
+        y = y + residual
+    return torch.relu_(y) if relu else y
 
 
 # -------------------------------------------------------------------- transformer

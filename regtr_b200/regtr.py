@@ -49,7 +49,13 @@ class CorrespondenceRegressor(nn.Module):
 
     def forward_packed(self, feats):
         """feats (L,N,E) packed -> corr (L,N,3), logits (L,N,1)."""
-        return self.coor_mlp(feats), self.conf_logits_decoder(feats)
+        L_, n, E = feats.shape
+        x = feats.reshape(L_ * n, E)
+        h = ops.linear(x, self.coor_mlp[0].weight, self.coor_mlp[0].bias, relu=True)
+        h = ops.linear(h, self.coor_mlp[2].weight, self.coor_mlp[2].bias, relu=True)
+        corr = ops.linear(h, self.coor_mlp[4].weight, self.coor_mlp[4].bias)
+        logit = ops.linear(x, self.conf_logits_decoder.weight, self.conf_logits_decoder.bias)
+        return corr.view(L_, n, 3), logit.view(L_, n, 1)
 
 
 class RegTR(nn.Module):
@@ -91,7 +97,7 @@ class RegTR(nn.Module):
         pts = meta['_points']
         feats0 = torch.ones_like(pts[0][:, 0:1])                                   # regtr.py:122
         feats_un, _ = self.kpf_encoder(feats0, meta)                               # regtr.py:136
-        both_un = self.feat_proj(feats_un)                                         # regtr.py:145
+        both_un = ops.linear(feats_un, self.feat_proj.weight, self.feat_proj.bias)  # regtr.py:145
         xyz_c = pts[-1]
         pe = self.pos_embed(xyz_c)                                                 # regtr.py:149-154
         cond = self.transformer_encoder.forward_packed(
@@ -143,10 +149,13 @@ class GraphedRegTR:
     to the eager forward, so results are never silently truncated.
     """
 
-    def __init__(self, model: RegTR, bucket: int = 8192, full_meta: bool = True):
+    def __init__(self, model: RegTR, bucket: int = 8192, full_meta: bool = True, ratio: float = 0.30,
+                 retry_ratio: float = 0.45):
         self.model = model
         self.bucket = int(bucket)
         self.full_meta = full_meta
+        self.ratio, self.retry_ratio = ratio, retry_ratio   # level-to-level capacity ratio (real data: 0.19-0.27)
+        self.ratios = {}
         self.graphs = {}
         self.fallbacks = 0
 
@@ -154,7 +163,7 @@ class GraphedRegTR:
         from .kpconv import level_capacities
         model = self.model
         dev = model.device
-        caps = level_capacities(model.cfg, cap0)
+        caps = level_capacities(model.cfg, cap0, ratio=self.ratios.get((B, cap0), self.ratio))
         st = dict(points=torch.zeros((cap0, 3), dtype=torch.float32, device=dev),
                   offs0=torch.zeros(2 * B + 1, dtype=torch.int32, device=dev), caps=caps)
 
@@ -218,8 +227,11 @@ class GraphedRegTR:
         n_lvl = len(pyr.levels)
         host = st['tail_host']
         code = int(host[-1])
-        if code & 2:                            # a level overflowed its capacity: redo eagerly
-            self.fallbacks += 1
+        if code & 2:                            # a level overflowed its capacity: redo eagerly and
+            self.fallbacks += 1                 # re-capture this bucket with more head-room next time
+            if self.ratios.get(key, self.ratio) < self.retry_ratio:
+                self.ratios[key] = self.retry_ratio
+                del self.graphs[key]
             return model.forward(batch)
         offs_host = host[:-1].reshape(n_lvl, 2 * B + 1)
         meta = model.preprocessor.finalize(pyr, host=(offs_host, code))

@@ -110,12 +110,12 @@ class TransformerCrossEncoderLayer(nn.Module):
         E = mha.embed_dim
         W, b = mha.in_proj_weight, mha.in_proj_bias
         if val_has_pos:
-            qkv = F.linear(x2p, W, b)                     # one packed in-projection GEMM
+            qkv = ops.linear(x2p, W, b)                   # one packed in-projection GEMM
             q, k, v = qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:]
         else:
-            qk = F.linear(x2p, W[:2 * E], b[:2 * E])
+            qk = ops.linear(x2p, W[:2 * E], b[:2 * E])
             q, k = qk[:, :E], qk[:, E:]
-            v = F.linear(x2, W[2 * E:], b[2 * E:])
+            v = ops.linear(x2, W[2 * E:], b[2 * E:])
         ks, kl = (plan.xk_start, plan.xk_len) if cross else (plan.q_start, plan.q_len)
         o = ops.mha_varlen(q, k, v, plan.q_start, plan.q_len, ks, kl, plan.max_len, self.nhead)
         return o
@@ -127,17 +127,17 @@ class TransformerCrossEncoderLayer(nn.Module):
         x2, x2p = ops.layernorm_pos(x, self.norm1.weight, self.norm1.bias, pos, self.norm1.eps,
                                     want_plain=not self.sa_val_has_pos_emb, want_pos=True)
         o = self._attend(self.self_attn, x2, x2p, self.sa_val_has_pos_emb or not has_pos, plan, cross=False)
-        x = torch.addmm(x, o, self.self_attn.out_proj.weight.t()).add_(self.self_attn.out_proj.bias)
+        x = ops.linear(o, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, residual=x)
         # cross attention, both directions from the same pre-update normalised features
         x2, x2p = ops.layernorm_pos(x, self.norm2.weight, self.norm2.bias, pos, self.norm2.eps,
                                     want_plain=not self.ca_val_has_pos_emb, want_pos=True)
         o = self._attend(self.multihead_attn, x2, x2p, self.ca_val_has_pos_emb or not has_pos, plan, cross=True)
-        x = torch.addmm(x, o, self.multihead_attn.out_proj.weight.t()).add_(self.multihead_attn.out_proj.bias)
+        x = ops.linear(o, self.multihead_attn.out_proj.weight, self.multihead_attn.out_proj.bias, residual=x)
         # position-wise feed-forward
         x2, _ = ops.layernorm_pos(x, self.norm3.weight, self.norm3.bias, None, self.norm3.eps,
                                   want_plain=True, want_pos=False)
-        h = F.relu_(F.linear(x2, self.linear1.weight, self.linear1.bias))
-        x = torch.addmm(x, h, self.linear2.weight.t()).add_(self.linear2.bias)
+        h = ops.linear(x2, self.linear1.weight, self.linear1.bias, relu=True)
+        x = ops.linear(h, self.linear2.weight, self.linear2.bias, residual=x)
         return x
 
 
