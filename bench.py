@@ -336,12 +336,17 @@ def main():
         torch.cuda.synchronize()
         tr, ops.KPCONV_TRACE = ops.KPCONV_TRACE, None
         tot_ms = sum(a.elapsed_time(b) for a, b, _ in tr)
+        gather_ms = sum(a.elapsed_time(info['mid']) if info.get('mid') is not None else a.elapsed_time(b)
+                        for a, b, info in tr)
         tot_bytes = sum(kpconv_algorithmic_bytes(info) for _, _, info in tr)
         peak, peak_src = peaks()
         ach = tot_bytes / (tot_ms * 1e-3) / 1e9
-        roof = dict(bound='hbm', kernel='regtr_kpconv_fwd (k_kpconv_agg gather/aggregate + weight GEMM), 11 calls/pair',
+        roof = dict(bound='hbm', kernel='KPConv op = k_kpconv_agg (neighbour gather + influence + aggregation) '
+                                        '+ weight contraction GEMM, 11 calls/pair',
                     achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=None, peak_source=peak_src,
                     algorithmic_bytes_per_step=tot_bytes / nsteps, kpconv_ms_per_step=tot_ms / nsteps,
+                    gather_kernel_ms_per_step=gather_ms / nsteps,
+                    gather_kernel_achieved_GBs=tot_bytes / (gather_ms * 1e-3) / 1e9,
                     launches_timed=len(tr))
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only)

@@ -151,9 +151,9 @@ def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=No
     nb = L.regtr_kpconv_ws_bytes(Nq, Ns, Cin)
     ws = workspace(nb, x.device, 'kpconv')
     trace = KPCONV_TRACE
-    if trace is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if trace is not None else None
+    if ev:
+        ev[0].record()
     if GEMM_BACKEND == 'tc3x' and (15 * Cin) % 4 == 0:
         # gather/aggregate kernel, then the [Nq,15Cin] x [15Cin,Cout] contraction on the tensor cores
         wf = ws[:Nq * 15 * Cin * 4].view(torch.float32).view(Nq, 15 * Cin)
@@ -163,15 +163,19 @@ def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=No
                                             _stream()), 'regtr_kpconv_aggregate')
         _count(2)
         hi, lo = split_weight(weights.view(15 * Cin, Cout), transpose=True)
+        if ev:
+            ev[1].record()
+            ev.append(True)
         gemm(wf, hi, lo, m_dev=nq_dev, out=out)
     else:
         _lib.check(L.regtr_kpconv_fwd(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(weights), _p(kernel_points), Nq, Ns,
                                       _p(nq_dev), _p(ns_dev), K, Cin, Cout, float(extent), _p(out), _p(ws),
                                       ws.numel(), _stream()), 'regtr_kpconv_fwd')
         _count(2)
-    if trace is not None:
-        e1.record()
-        trace.append((e0, e1, dict(Nq=Nq, Ns=Ns, K=K, Cin=Cin, Cout=Cout, idx=idx32)))
+    if ev:
+        ev[2].record()
+        trace.append((ev[0], ev[2], dict(Nq=Nq, Ns=Ns, K=K, Cin=Cin, Cout=Cout, idx=idx32,
+                                         mid=ev[1] if len(ev) > 3 else None)))
     return out
 
 
@@ -218,24 +222,24 @@ def instnorm_act(x, offs, n_clouds: int, res=None, slope: float = -1.0, eps: flo
 
 # -------------------------------------------------------------------- dense layers
 
-_split_cache = {}
-
-
 def split_weight(w: torch.Tensor, transpose: bool = False):
-    """(hi, lo) TF32 halves of a weight matrix [N,K] (or of its transpose), cached per parameter
-    storage + version so that inference pays the split once."""
+    """(hi, lo) TF32 halves of a weight matrix [N,K] (or of its transpose).  Cached ON the owning
+    parameter object (so the cache dies with the model and can never alias a recycled address),
+    keyed by view geometry and the parameter's version counter: inference pays the split once."""
     L = _lib.load()
-    key = (w.data_ptr(), w._version, tuple(w.shape), transpose)
-    hit = _split_cache.get(key)
+    owner = w._base if w._base is not None else w
+    cache = owner.__dict__.setdefault('_regtr_split', {})
+    key = (w.storage_offset(), tuple(w.shape), tuple(w.stride()), transpose, owner._version)
+    hit = cache.get(key)
     if hit is not None:
         return hit
     src = (w.detach().t() if transpose else w.detach()).contiguous().to(torch.float32)
     hi, lo = torch.empty_like(src), torch.empty_like(src)
     _lib.check(L.regtr_split_tf32(_p(src), src.numel(), _p(hi), _p(lo), _stream()), 'regtr_split_tf32')
     _count(1)
-    if len(_split_cache) > 4096:
-        _split_cache.clear()
-    _split_cache[key] = (hi, lo)
+    for k in [k for k in cache if k[-1] != owner._version]:
+        del cache[k]
+    cache[key] = (hi, lo)
     return hi, lo
 
 

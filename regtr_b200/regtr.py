@@ -214,9 +214,9 @@ class GraphedRegTR:
             offs.append(offs[-1] + v)
         if clouds[0].is_cuda:
             torch.cat(clouds, dim=0, out=st['points'][:n0])
-        else:                                   # host clouds: pack into pinned staging, one H2D
-            torch.cat(clouds, dim=0, out=st['stage'][:n0])
-            st['points'][:n0].copy_(st['stage'][:n0], non_blocking=True)
+        else:                                   # host clouds: asynchronous H2D straight into the packed buffer
+            for c, a in zip(clouds, offs):      # (pinned sources copy without a staging pass)
+                st['points'][a:a + c.shape[0]].copy_(c, non_blocking=True)
         st['offs0'].copy_(torch.tensor(offs, dtype=torch.int32), non_blocking=True)
         # ---- replay + the single D2H / sync
         st['graph'].replay()
