@@ -31,6 +31,12 @@ template <int BN, int ST> struct Cfg {
     static constexpr int B_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    // The tensor core adds into its fp32 accumulator with truncation, so a long run of
+    // accumulations drifts (measured: error grows ~linearly with K).  The k-steps of a k-block
+    // are therefore spread over NACC independent TMEM accumulators that are summed with
+    // round-to-nearest fp32 adds in the epilogue (4x fewer hardware accumulations each).
+    static constexpr int NACC = (BN == 128 && ST == 2) ? 2 : 4;   // 2 CTAs/SM must share 512 columns
+    static constexpr int TMEM_COLS = NACC * BN;
 };
 
 // round-to-nearest-even to TF32 precision (10 mantissa bits); unbiased, so split errors do not
@@ -80,7 +86,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&tmA); tc::tma_prefetch_desc(&tmBhi); tc::tma_prefetch_desc(&tmBlo);
     }
-    if (warp == 1) tc::tmem_alloc<BN>(tmem_slot);
+    if (warp == 1) tc::tmem_alloc<P::TMEM_COLS>(tmem_slot);
     tc::fence_before_thread_sync();
     __syncthreads();
     tc::fence_after_thread_sync();
@@ -118,9 +124,11 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {             // UMMA_K = 8 tf32 = 32 bytes
                     const uint64_t adv = (uint64_t)((k * 32) >> 4);
-                    tc::umma_tf32(tmem_d, dAlo + adv, dBhi + adv, idesc, (kb | k) != 0);   // small terms first
-                    tc::umma_tf32(tmem_d, dA + adv, dBlo + adv, idesc, 1);
-                    tc::umma_tf32(tmem_d, dA + adv, dBhi + adv, idesc, 1);
+                    const uint32_t acc = tmem_d + (uint32_t)((k % P::NACC) * BN);
+                    const uint32_t first = (kb == 0 && k < P::NACC) ? 0u : 1u;
+                    tc::umma_tf32(acc, dAlo + adv, dBhi + adv, idesc, first);   // small terms first
+                    tc::umma_tf32(acc, dA + adv, dBlo + adv, idesc, 1);
+                    tc::umma_tf32(acc, dA + adv, dBhi + adv, idesc, 1);
                 }
                 tc::umma_commit(&empty[s]);
             }
@@ -156,6 +164,13 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int c0 = 0; c0 < BN; c0 += 32) {
             float v[32];
             tc::tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int a = 1; a < P::NACC; ++a) {
+                float u[32];
+                tc::tmem_ld_32x32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0), u);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += u[j];
+            }
             const int col0 = n0 + c0;
             if (!row_ok || col0 >= N) continue;
             if (col0 + 32 <= N && (ldc & 3) == 0 && (!R || (ldr & 3) == 0)) {
@@ -180,7 +195,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     tc::fence_before_thread_sync();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc<BN>(tmem_d);
+    if (warp == 1) tc::tmem_dealloc<P::TMEM_COLS>(tmem_d);
 }
 
 // C = act(sum_z P[z] + bias + R): deterministic split-K reduction (fixed order), 4 columns / thread

@@ -259,7 +259,7 @@ def test_forward_is_deterministic_and_batch_invariant():
     o3, m3 = _run_model(cfg, sd, [p['src_xyz'] for p in ps], [p['tgt_xyz'] for p in ps])
     assert torch.equal(o1['pose'], o1b['pose'])
     assert torch.equal(o1['src_kp'][0], o3['src_kp'][1])
-    assert float((o1['pose'][:, 0] - o3['pose'][:, 1]).abs().max()) <= 2e-5
+    assert float((o1['pose'][:, 0] - o3['pose'][:, 1]).abs().max()) <= 5e-5   # tile shapes differ with M
 
 
 def test_graphed_executor_matches_eager_and_survives_overflow():
@@ -288,7 +288,7 @@ def test_graphed_executor_matches_eager_and_survives_overflow():
         assert torch.equal(got['src_kp'][0], want['src_kp'][0])
         s = float(want['src_feat'][0].abs().max())
         assert float((got['src_feat'][0] - want['src_feat'][0]).abs().max()) <= 2e-5 * s
-        assert float((got['pose'] - want['pose']).abs().max()) <= 2e-5
+        assert float((got['pose'] - want['pose']).abs().max()) <= 5e-5     # two fp32-accurate evaluation orders
         assert torch.equal(got['pose_host'], got['pose'].cpu())
     assert len(runner.graphs) == 1 and runner.fallbacks == 0
     # volume-filling cloud: every point its own voxel -> level 1 does not fit 0.4 * cap0 -> eager fallback
