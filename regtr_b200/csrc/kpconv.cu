@@ -29,25 +29,21 @@ __global__ void k_row_flags(const float* __restrict__ x, int n, int C, uint8_t* 
     if (lane == 0) flags[warp] = acc > 0.0;
 }
 
-__device__ __forceinline__ void influences(float rx, float ry, float rz, const float* __restrict__ kp_s,
-                                           float inv_dummy, float extent, float* __restrict__ w) {
-    (void)inv_dummy;
-#pragma unroll
-    for (int p = 0; p < KP; ++p) {
-        const float dx = rx - kp_s[3 * p + 0], dy = ry - kp_s[3 * p + 1], dz = rz - kp_s[3 * p + 2];
-        const float d2 = dx * dx + dy * dy + dz * dz;
-        w[p] = fmaxf(0.f, 1.f - sqrtf(d2) / extent);
-    }
-}
+// ---- packed fp32x2 FMA (sm_100: one instruction, two FMAs)
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 f2_dup(float x) { f2 r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(x)); return r; }
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ void f2_unpack(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 
-// Phase 1 shared by both aggregation kernels: lanes own neighbours, compute the 15
-// influences, compact the valid (non-shadow) neighbours into shared memory.
-// Returns (n_valid, neighbour_count) to every lane.
+// Phase 1 (lanes own neighbours): compact the valid (non-shadow) neighbours of one query into
+// shared memory as (relative position, id) and count those whose feature row sums to > 0.
+// Phase 2 (lanes own (neighbour, kernel point) pairs, 16 per neighbour so that all 32 lanes stay
+// busy): linear influence  h = max(0, 1 - |rel - kp| / extent)  into w_s[k][16] (slot 15 = 0).
 __device__ __forceinline__ void stage_neighbours(const float* __restrict__ s, const int32_t* __restrict__ idx_row,
                                                  const uint8_t* __restrict__ flags, const float* __restrict__ kp_s,
-                                                 float qx, float qy, float qz, int Ns, int K, float extent,
-                                                 float* __restrict__ w_s, int* __restrict__ id_s, int lane,
-                                                 int& n_valid, int& n_counted) {
+                                                 float qx, float qy, float qz, int Ns, int K, float inv_extent,
+                                                 float* __restrict__ w_s, float4* __restrict__ rel_s,
+                                                 int* __restrict__ id_s, int lane, int& n_valid, int& n_counted) {
     int base = 0, counted = 0;
     for (int k0 = 0; k0 < K; k0 += 32) {
         const int kk = k0 + lane;
@@ -57,13 +53,7 @@ __device__ __forceinline__ void stage_neighbours(const float* __restrict__ s, co
         const unsigned m = __ballot_sync(0xffffffffu, valid);
         if (valid) {
             const int pos = base + __popc(m & ((1u << lane) - 1u));
-            float w[KP];
-            influences(s[3 * id + 0] - qx, s[3 * id + 1] - qy, s[3 * id + 2] - qz, kp_s, 0.f, extent, w);
-            float4* dst = reinterpret_cast<float4*>(w_s + pos * KPP);
-            dst[0] = make_float4(w[0], w[1], w[2], w[3]);
-            dst[1] = make_float4(w[4], w[5], w[6], w[7]);
-            dst[2] = make_float4(w[8], w[9], w[10], w[11]);
-            dst[3] = make_float4(w[12], w[13], w[14], 0.f);
+            rel_s[pos] = make_float4(s[3 * id + 0] - qx, s[3 * id + 1] - qy, s[3 * id + 2] - qz, 0.f);
             id_s[pos] = id;
             counted += flags[id];
         }
@@ -72,14 +62,27 @@ __device__ __forceinline__ void stage_neighbours(const float* __restrict__ s, co
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, o);
     __syncwarp();
+    for (int t = lane; t < base * KPP; t += 32) {
+        const int k = t >> 4, p = t & 15;
+        float w = 0.f;
+        if (p < KP) {
+            const float4 r = rel_s[k];
+            const float dx = r.x - kp_s[3 * p + 0], dy = r.y - kp_s[3 * p + 1], dz = r.z - kp_s[3 * p + 2];
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            const float d = d2 > 0.f ? d2 * rsqrtf(d2) : 0.f;          // |.|: <= 2 ulp, far inside the tolerance
+            w = fmaxf(0.f, 1.f - d * inv_extent);
+        }
+        w_s[t] = w;
+    }
+    __syncwarp();
     n_valid = base;
     n_counted = counted;
 }
 
-// Cin multiple of 32: lane owns VEC channels; per valid neighbour one coalesced row load
-// and 15*VEC FMAs against influences broadcast from shared memory.
-template <int VEC, int UNROLL>
-__global__ void __launch_bounds__(AGG_WARPS * 32)
+// Cin = 32 * VEC: lane owns VEC channels; per valid neighbour one coalesced row load, four
+// broadcast LDS.128 of the 16 influences and 8 * VEC packed fp32x2 FMAs.
+template <int VEC, int UNROLL, int MINB>
+__global__ void __launch_bounds__(AGG_WARPS * 32, MINB)
 k_kpconv_agg(const float* __restrict__ q, const float* __restrict__ s, const int32_t* __restrict__ idx,
              const float* __restrict__ x, const uint8_t* __restrict__ flags, const float* __restrict__ kp,
              int Nq, int Ns, const int32_t* __restrict__ nq_dev, const int32_t* __restrict__ ns_dev, int K,
@@ -90,8 +93,9 @@ k_kpconv_agg(const float* __restrict__ q, const float* __restrict__ s, const int
     float* kp_s = reinterpret_cast<float*>(smem_raw);     // 48 floats
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Kp = (K + 3) & ~3;
-    float* w_s = kp_s + 48 + warp * (Kp * KPP);
-    int* id_s = reinterpret_cast<int*>(kp_s + 48 + AGG_WARPS * (Kp * KPP)) + warp * Kp;
+    float* w_s = kp_s + 48 + warp * (Kp * (KPP + 4 + 1));            // per warp: w[Kp][16] | rel[Kp] (float4) | id[Kp]
+    float4* rel_s = reinterpret_cast<float4*>(w_s + Kp * KPP);
+    int* id_s = reinterpret_cast<int*>(w_s + Kp * (KPP + 4));
     if (threadIdx.x < 3 * KP) kp_s[threadIdx.x] = kp[threadIdx.x];
     __syncthreads();
     const int qi = blockIdx.x * AGG_WARPS + warp;
@@ -104,14 +108,14 @@ k_kpconv_agg(const float* __restrict__ q, const float* __restrict__ s, const int
     }
 
     int n_valid, n_counted;
-    stage_neighbours(s, idx + (size_t)qi * K, flags, kp_s, q[3 * qi], q[3 * qi + 1], q[3 * qi + 2], Ns, K, extent,
-                     w_s, id_s, lane, n_valid, n_counted);
+    stage_neighbours(s, idx + (size_t)qi * K, flags, kp_s, q[3 * qi], q[3 * qi + 1], q[3 * qi + 2], Ns, K,
+                     1.f / extent, w_s, rel_s, id_s, lane, n_valid, n_counted);
 
-    float acc[KP][VEC];
+    f2 acc[8][VEC];                               // acc[j] = kernel points (2j, 2j+1); slot 15 is padding
 #pragma unroll
-    for (int p = 0; p < KP; ++p)
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[p][v] = 0.f;
+        for (int v = 0; v < VEC; ++v) acc[j][v] = 0ull;
 
     for (int k0 = 0; k0 < n_valid; k0 += UNROLL) {
         float xv[UNROLL][VEC];
@@ -135,43 +139,55 @@ k_kpconv_agg(const float* __restrict__ q, const float* __restrict__ s, const int
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             if (k0 + u < n_valid) {
-                const float4* wr = reinterpret_cast<const float4*>(w_s + (k0 + u) * KPP);
-                const float4 a = wr[0], b = wr[1], c = wr[2], d = wr[3];
-                const float w[KP] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z};
+                const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(w_s + (k0 + u) * KPP);
+                const ulonglong2 a = wr[0], b = wr[1], c = wr[2], d = wr[3];
+                const f2 w2[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
 #pragma unroll
-                for (int p = 0; p < KP; ++p)
+                for (int v = 0; v < VEC; ++v) {
+                    const f2 xx = f2_dup(xv[u][v]);
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) acc[p][v] = fmaf(w[p], xv[u][v], acc[p][v]);
+                    for (int j = 0; j < 8; ++j) acc[j][v] = f2_fma(w2[j], xx, acc[j][v]);
+                }
             }
         }
     }
 
     const float inv = 1.f / (float)max(n_counted, 1);
     float* out = wf + (size_t)qi * (KP * CIN);
+    float r[KPP][VEC];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) f2_unpack(acc[j][v], r[2 * j][v], r[2 * j + 1][v]);
 #pragma unroll
     for (int p = 0; p < KP; ++p) {
         if constexpr (VEC == 1) {
-            out[p * CIN + lane] = acc[p][0] * inv;
+            out[p * CIN + lane] = r[p][0] * inv;
         } else if constexpr (VEC == 2) {
-            reinterpret_cast<float2*>(out + p * CIN)[lane] = make_float2(acc[p][0] * inv, acc[p][1] * inv);
+            reinterpret_cast<float2*>(out + p * CIN)[lane] = make_float2(r[p][0] * inv, r[p][1] * inv);
         } else {
 #pragma unroll
             for (int j = 0; j < NV4; ++j)
                 reinterpret_cast<float4*>(out + p * CIN)[j * 32 + lane] =
-                    make_float4(acc[p][4 * j] * inv, acc[p][4 * j + 1] * inv, acc[p][4 * j + 2] * inv,
-                                acc[p][4 * j + 3] * inv);
+                    make_float4(r[p][4 * j] * inv, r[p][4 * j + 1] * inv, r[p][4 * j + 2] * inv, r[p][4 * j + 3] * inv);
         }
     }
 }
 
-// Small Cin (1..16): lanes own neighbours all the way, channel sums by warp shuffle.
+// Small Cin (1..16, e.g. the constant-1 input feature of the first block): same staging; then lane
+// (p, half) sums w[k][p] * x[id_k][c] over its half of the neighbours, halves combined by shuffle.
 __global__ void __launch_bounds__(AGG_WARPS * 32)
 k_kpconv_agg_small(const float* __restrict__ q, const float* __restrict__ s, const int32_t* __restrict__ idx,
                    const float* __restrict__ x, const uint8_t* __restrict__ flags, const float* __restrict__ kp,
                    int Nq, int Ns, const int32_t* __restrict__ nq_dev, const int32_t* __restrict__ ns_dev, int K, int Cin,
                    float extent, float* __restrict__ wf) {
-    __shared__ float kp_s[48];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* kp_s = reinterpret_cast<float*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Kp = (K + 3) & ~3;
+    float* w_s = kp_s + 48 + warp * (Kp * (KPP + 4 + 1));
+    float4* rel_s = reinterpret_cast<float4*>(w_s + Kp * KPP);
+    int* id_s = reinterpret_cast<int*>(w_s + Kp * (KPP + 4));
     if (threadIdx.x < 3 * KP) kp_s[threadIdx.x] = kp[threadIdx.x];
     __syncthreads();
     const int qi = blockIdx.x * AGG_WARPS + warp;
@@ -182,38 +198,16 @@ k_kpconv_agg_small(const float* __restrict__ q, const float* __restrict__ s, con
         for (int t = lane; t < KP * Cin; t += 32) out[t] = 0.f;
         return;
     }
-    const float qx = q[3 * qi], qy = q[3 * qi + 1], qz = q[3 * qi + 2];
-    int counted = 0;
+    int n_valid, n_counted;
+    stage_neighbours(s, idx + (size_t)qi * K, flags, kp_s, q[3 * qi], q[3 * qi + 1], q[3 * qi + 2], Ns, K,
+                     1.f / extent, w_s, rel_s, id_s, lane, n_valid, n_counted);
+    const float inv = 1.f / (float)max(n_counted, 1);
+    const int p = lane & 15, half = lane >> 4;
     for (int c = 0; c < Cin; ++c) {
-        float accp[KP];
-#pragma unroll
-        for (int p = 0; p < KP; ++p) accp[p] = 0.f;
-        for (int k0 = 0; k0 < K; k0 += 32) {
-            const int kk = k0 + lane;
-            int id = Ns;
-            if (kk < K) id = idx[(size_t)qi * K + kk];
-            if (id >= 0 && id < Ns) {
-                float w[KP];
-                influences(s[3 * id] - qx, s[3 * id + 1] - qy, s[3 * id + 2] - qz, kp_s, 0.f, extent, w);
-                const float xv = x[(size_t)id * Cin + c];
-#pragma unroll
-                for (int p = 0; p < KP; ++p) accp[p] = fmaf(w[p], xv, accp[p]);
-                if (c == 0) counted += flags[id];
-            }
-        }
-#pragma unroll
-        for (int p = 0; p < KP; ++p) accp[p] = warp_sum(accp[p]);
-        if (c == 0) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, o);
-        }
-        const float inv = 1.f / (float)max(counted, 1);
-        if (lane < KP) {
-            float v = 0.f;
-#pragma unroll
-            for (int p = 0; p < KP; ++p) v = (lane == p) ? accp[p] : v;
-            out[lane * Cin + c] = v * inv;
-        }
+        float acc = 0.f;
+        for (int k = half; k < n_valid; k += 2) acc = fmaf(w_s[k * KPP + p], __ldg(x + (size_t)id_s[k] * Cin + c), acc);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if (lane < KP) out[lane * Cin + c] = acc * inv;
     }
 }
 
@@ -267,21 +261,21 @@ cublasHandle_t get_handle() {
 
 size_t agg_smem_bytes(int K) {
     const int Kp = (K + 3) & ~3;
-    return sizeof(float) * 48 + (size_t)AGG_WARPS * Kp * (KPP * sizeof(float) + sizeof(int));
+    return sizeof(float) * 48 + (size_t)AGG_WARPS * Kp * (KPP + 4 + 1) * sizeof(float);
 }
 
-template <int VEC, int UNROLL>
+template <int VEC, int UNROLL, int MINB>
 int launch_agg(const float* q, const float* s, const int32_t* idx, const float* x, const uint8_t* flags,
                const float* kp, int Nq, int Ns, const int32_t* nq_dev, const int32_t* ns_dev, int K, float extent,
                float* wf, cudaStream_t st) {
     const size_t smem = agg_smem_bytes(K);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_kpconv_agg<VEC, UNROLL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_kpconv_agg<VEC, UNROLL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return -(1000 + (int)e);
     }
-    k_kpconv_agg<VEC, UNROLL><<<regtr_cdiv(Nq, AGG_WARPS), AGG_WARPS * 32, smem, st>>>(q, s, idx, x, flags, kp, Nq, Ns,
-                                                                                     nq_dev, ns_dev, K, extent, wf);
+    k_kpconv_agg<VEC, UNROLL, MINB><<<regtr_cdiv(Nq, AGG_WARPS), AGG_WARPS * 32, smem, st>>>(
+        q, s, idx, x, flags, kp, Nq, Ns, nq_dev, ns_dev, K, extent, wf);
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
 }
@@ -309,16 +303,18 @@ int regtr_kpconv_aggregate(const float* q, const float* s, const int32_t* idx, c
         REGTR_CHECK_LAUNCH();
     }
     if (Cin <= 16) {
-        k_kpconv_agg_small<<<regtr_cdiv(Nq, AGG_WARPS), AGG_WARPS * 32, 0, st>>>(q, s, idx, x, rowflag_ws, kp, Nq, Ns,
-                                                                                nq_dev, ns_dev, K, Cin, extent, wf);
+        const size_t smem = agg_smem_bytes(K);
+        if (smem > 48 * 1024) return REGTR_ERR_UNSUPPORTED;
+        k_kpconv_agg_small<<<regtr_cdiv(Nq, AGG_WARPS), AGG_WARPS * 32, smem, st>>>(q, s, idx, x, rowflag_ws, kp, Nq,
+                                                                                   Ns, nq_dev, ns_dev, K, Cin, extent, wf);
         REGTR_CHECK_LAUNCH();
         return REGTR_OK;
     }
     switch (Cin / 32) {
-        case 1: return launch_agg<1, 4>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, extent, wf, st);
-        case 2: return launch_agg<2, 4>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, extent, wf, st);
-        case 4: return launch_agg<4, 4>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, extent, wf, st);
-        case 8: return launch_agg<8, 2>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, extent, wf, st);
+        case 1: return launch_agg<1, 4, 5>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, extent, wf, st);
+        case 2: return launch_agg<2, 4, 4>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, extent, wf, st);
+        case 4: return launch_agg<4, 4, 2>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, extent, wf, st);
+        case 8: return launch_agg<8, 2, 1>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, extent, wf, st);
     }
     return REGTR_ERR_UNSUPPORTED;
 }

@@ -175,7 +175,8 @@ def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=No
     if ev:
         ev[2].record()
         trace.append((ev[0], ev[2], dict(Nq=Nq, Ns=Ns, K=K, Cin=Cin, Cout=Cout, idx=idx32,
-                                         mid=ev[1] if len(ev) > 3 else None)))
+                                         mid=ev[1] if len(ev) > 3 else None,
+                                         args=(q_pts, s_pts, idx32, x, kernel_points, float(extent)))))
     return out
 
 
