@@ -55,6 +55,8 @@ def parse():
     ap.add_argument('--pairs', type=int, default=None, help='pairs per GPU per step (default: from config)')
     ap.add_argument('--cpu-baseline', type=int, default=1, help='time the CPU port beside the GPU run (N=1 only)')
     ap.add_argument('--checks', type=int, default=1, help='report pose error vs the oracle on one pair')
+    ap.add_argument('--attention', default='fp32', choices=['fp32', 'bf16_tc'],
+                    help="fp32: parity kernel (default, pose within 1e-4); bf16_tc: tcgen05 tensor-core core")
     ap.add_argument('--graph', type=int, default=1, help='1: CUDA-graph executor (GraphedRegTR); 0: eager forward')
     return ap.parse_args()
 
@@ -240,6 +242,7 @@ def main():
     B = pairs_per_gpu(args)
 
     cfg = get_config('3dmatch')
+    cfg.attention_impl = args.attention
     sd = random_state_dict(cfg, WEIGHT_SEED)
     model = RegTR(cfg).to(dev).eval()
     model.load_state_dict(sd, strict=True)
@@ -393,7 +396,8 @@ def main():
             dtype='f32', data='synthetic',
             config=dict(workload=workload_name(args, B), pairs_per_gpu_per_step=B,
                         parallelism=f'pair-level data parallel x{world}', l2_flush_between_steps=True,
-                        weights='seeded random init (no pretrained weights offline)', precision_mode='fp32 parity',
+                        weights='seeded random init (no pretrained weights offline)', precision_mode='fp32 parity (3xTF32 tcgen05 GEMMs, fp32 attention)' if args.attention == 'fp32'
+                        else 'fast (3xTF32 GEMMs, bf16 tcgen05 attention core)',
                         executor='cuda-graph (GraphedRegTR)' if args.graph else 'eager'),
             e2e=dict(value=pairs / (t_e2e_ms * 1e-3), unit='pairs/s', h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h, ms_per_step=t_e2e_ms / K),

@@ -173,6 +173,19 @@ int regtr_mha_varlen_fwd(const float* Q, int ldq, const float* K, int ldk, const
                          const int32_t* k_start, const int32_t* k_len, int n_problems,
                          int max_q_len, int n_heads, int head_dim, float scale, void* stream);
 
+/* Tensor-core attention core (bf16 operands, fp32 TMEM accumulation, fp32 softmax): the "fast"
+ * precision mode of the same nn.MultiheadAttention core (transformers.py:197-226), head_dim 32.
+ * Inputs are produced by regtr_gemm_tf32x3_qkv_bf16 (the packed in-projection with a bf16
+ * epilogue): QK [n_tokens, 2E] bf16 row-major (q | k), Vt [E, ld_vt] bf16 (v transposed, columns
+ * >= n_tokens zero).  O [n_tokens, E] fp32.  Problem tables as for regtr_mha_varlen_fwd. */
+int regtr_gemm_tf32x3_qkv_bf16(const float* A, int lda, const float* B_hi, const float* B_lo, int ldb,
+                               const float* bias, int M, int N, int K, int split, void* qk_out, int ld_qk,
+                               void* vt_out, int ld_vt, const int32_t* m_dev, void* stream);
+int regtr_mha_bf16_tc_fwd(const void* QK, int ld_qk, const void* Vt, int ld_vt, int n_tokens, float* O,
+                          int ldo, const int32_t* q_start, const int32_t* q_len, const int32_t* k_start,
+                          const int32_t* k_len, int n_problems, int max_q_len, int n_heads, int head_dim,
+                          float scale, void* stream);
+
 /* ---- pose ------------------------------------------------------------------------- */
 
 /* Weighted Kabsch.  Replaces compute_rigid_transform (utils/se3_torch.py:108-154):

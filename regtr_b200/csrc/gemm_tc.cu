@@ -16,10 +16,22 @@
 //   warps 2-5  operand split (A -> A_hi in place, A_lo to a second buffer) between TMA arrival
 //              and MMA issue, then the epilogue: TMEM -> registers -> bias/residual/ReLU -> global
 // B (weights) is split once on the host side of the ABI (regtr_split_tf32) and cached.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "tc.cuh"
 
 namespace {
+
+// Optional bf16 epilogue for the attention in-projection: columns [0, split) are written row-major
+// to `qk` (the q and k halves), columns >= split transposed to `vt` (one row per channel).
+struct QkvOut {
+    __nv_bfloat16* qk;
+    int ld_qk;
+    __nv_bfloat16* vt;
+    int ld_vt;
+    int split;
+};
 
 constexpr int BM = 128;
 constexpr int BK = 32;                       // fp32 elements = 128 bytes = one swizzle span
@@ -60,7 +72,7 @@ __global__ void __launch_bounds__(192, ST == 2 ? 2 : 1)
 k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
               const __grid_constant__ CUtensorMap tmBlo, float* __restrict__ C, int ldc,
               const float* __restrict__ bias, const float* __restrict__ R, int ldr, int M, int N, int K,
-              const int32_t* __restrict__ m_dev, int relu, int kb_per_split, size_t split_stride) {
+              const int32_t* __restrict__ m_dev, int relu, int kb_per_split, size_t split_stride, QkvOut qkv) {
     using P = Cfg<BN, ST>;
     extern __shared__ unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -173,6 +185,28 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
             const int col0 = n0 + c0;
             if (!row_ok || col0 >= N) continue;
+            if (qkv.qk) {                                      // bf16 epilogue (N % 32 == 0 guaranteed by the host)
+                if (bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += bias[col0 + j];
+                }
+                if (col0 < qkv.split) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        pk[j] = *reinterpret_cast<const uint32_t*>(&b);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(qkv.qk + (size_t)row * qkv.ld_qk + col0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        qkv.vt[(size_t)(col0 - qkv.split + j) * qkv.ld_vt + row] = __float2bfloat16_rn(v[j]);
+                }
+                continue;
+            }
             if (col0 + 32 <= N && (ldc & 3) == 0 && (!R || (ldr & 3) == 0)) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -273,7 +307,7 @@ bool make_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld, int 
 template <int BN, int ST>
 int launch_gemm(const float* A, int lda, const float* Bhi, const float* Blo, int ldb, float* C, int ldc,
                 const float* bias, const float* R, int ldr, int M, int N, int K, const int32_t* m_dev, int relu,
-                int splits, float* ws, cudaStream_t st) {
+                int splits, float* ws, cudaStream_t st, QkvOut qkv = QkvOut{nullptr, 0, nullptr, 0, 0}) {
     CUtensorMap tA, tBh, tBl;
     if (!make_map(&tA, A, M, K, lda, BM) || !make_map(&tBh, Bhi, N, K, ldb, BN) || !make_map(&tBl, Blo, N, K, ldb, BN))
         return REGTR_ERR_ARG;
@@ -288,7 +322,7 @@ int launch_gemm(const float* A, int lda, const float* Bhi, const float* Blo, int
     if (splits <= 1) {
         dim3 grid(regtr_cdiv(M, BM), regtr_cdiv(N, BN), 1);
         k_gemm_tf32x3<BN, ST><<<grid, 192, Cfg<BN, ST>::SMEM, st>>>(tA, tBh, tBl, C, ldc, bias, R, ldr, M, N, K, m_dev,
-                                                                    relu, nkb, 0);
+                                                                    relu, nkb, 0, qkv);
         REGTR_CHECK_LAUNCH();
         return REGTR_OK;
     }
@@ -297,7 +331,7 @@ int launch_gemm(const float* A, int lda, const float* Bhi, const float* Blo, int
     const size_t stride = (size_t)M * N;
     dim3 grid(regtr_cdiv(M, BM), regtr_cdiv(N, BN), z);
     k_gemm_tf32x3<BN, ST><<<grid, 192, Cfg<BN, ST>::SMEM, st>>>(tA, tBh, tBl, ws, N, nullptr, nullptr, 0, M, N, K, m_dev, 0,
-                                                                per, stride);
+                                                                per, stride, QkvOut{nullptr, 0, nullptr, 0, 0});
     REGTR_CHECK_LAUNCH();
     k_splitk_reduce<<<regtr_cdiv((long long)M * (N / 4), 256), 256, 0, st>>>(ws, z, stride, C, ldc, bias, R, ldr, M, N,
                                                                             m_dev, relu);
@@ -349,6 +383,24 @@ int regtr_gemm_tf32x3(const float* A, int lda, const float* B_hi, const float* B
     if (shortk) REGTR_GEMM_CASE(32, 2);
     REGTR_GEMM_CASE(32, 4);
 #undef REGTR_GEMM_CASE
+}
+
+// In-projection of the attention block with the bf16 epilogue consumed by regtr_mha_bf16_tc_fwd:
+// qk_out [M, split] bf16 (ld_qk), vt_out [N - split, ld_vt] bf16 (transposed v), bias added first.
+int regtr_gemm_tf32x3_qkv_bf16(const float* A, int lda, const float* B_hi, const float* B_lo, int ldb,
+                               const float* bias, int M, int N, int K, int split, void* qk_out, int ld_qk,
+                               void* vt_out, int ld_vt, const int32_t* m_dev, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (M < 0 || N <= 0 || K <= 0 || split <= 0 || split > N) return REGTR_ERR_ARG;
+    if (M == 0) return REGTR_OK;
+    if (!A || !B_hi || !B_lo || !qk_out || !vt_out) return REGTR_ERR_ARG;
+    if ((N & 31) || (split & 31) || (ld_qk & 7) || ((uintptr_t)qk_out & 15) || (lda & 3) || (ldb & 3) ||
+        ((uintptr_t)A & 15) || ((uintptr_t)B_hi & 15) || ((uintptr_t)B_lo & 15) || ld_vt < M)
+        return REGTR_ERR_UNSUPPORTED;
+    QkvOut q{(__nv_bfloat16*)qk_out, ld_qk, (__nv_bfloat16*)vt_out, ld_vt, split};
+    float* dummy = reinterpret_cast<float*>(qk_out);      // C is never written in this mode
+    if (K <= 128) return launch_gemm<32, 2>(A, lda, B_hi, B_lo, ldb, dummy, 0, bias, nullptr, 0, M, N, K, m_dev, 0, 1, nullptr, st, q);
+    return launch_gemm<32, 4>(A, lda, B_hi, B_lo, ldb, dummy, 0, bias, nullptr, 0, M, N, K, m_dev, 0, 1, nullptr, st, q);
 }
 
 }  // extern "C"

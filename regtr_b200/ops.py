@@ -352,6 +352,28 @@ def mha_varlen(q, k, v, q_start, q_len, k_start, k_len, max_q_len: int, n_heads:
     return out
 
 
+def mha_bf16_tc(x, in_w, in_b, q_start, q_len, k_start, k_len, max_q_len: int, n_heads: int, m_dev=None):
+    """Attention block core in the fast precision mode: packed in-projection (3xTF32 GEMM, bf16
+    epilogue) + tcgen05 bf16 attention.  x (N,E) fp32 (already LN + pos); returns O (N,E) fp32."""
+    L = _lib.load()
+    _chk(x, torch.float32, 'x', 2)
+    N, E = x.shape
+    dh = E // n_heads
+    hi, lo = split_weight(in_w)
+    ld_vt = (N + 63) // 64 * 64 + 64            # token pitch of the transposed V (TMA: 16-byte multiple)
+    qk = torch.empty((N, 2 * E), dtype=torch.bfloat16, device=x.device)
+    vt = torch.zeros((E, ld_vt), dtype=torch.bfloat16, device=x.device)
+    _lib.check(L.regtr_gemm_tf32x3_qkv_bf16(_p(x), x.stride(0), _p(hi), _p(lo), hi.stride(0), _p(in_b), N, 3 * E, E,
+                                            2 * E, _p(qk), 2 * E, _p(vt), ld_vt, _p(m_dev), _stream()),
+               'regtr_gemm_tf32x3_qkv_bf16')
+    out = torch.zeros((N, E), dtype=torch.float32, device=x.device)
+    _lib.check(L.regtr_mha_bf16_tc_fwd(_p(qk), 2 * E, _p(vt), ld_vt, N, _p(out), E, _p(q_start), _p(q_len),
+                                       _p(k_start), _p(k_len), q_start.numel(), int(max_q_len), n_heads, dh,
+                                       1.0 / math.sqrt(dh), _stream()), 'regtr_mha_bf16_tc_fwd')
+    _count(2)
+    return out
+
+
 # --------------------------------------------------------------------------- pose
 
 def kabsch(a, b, w, offs):

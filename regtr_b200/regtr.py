@@ -73,7 +73,8 @@ class RegTR(nn.Module):
         layer = TransformerCrossEncoderLayer(
             cfg.d_embed, cfg.nhead, cfg.d_feedforward, cfg.dropout, activation=cfg.transformer_act,
             normalize_before=cfg.pre_norm, sa_val_has_pos_emb=cfg.sa_val_has_pos_emb,
-            ca_val_has_pos_emb=cfg.ca_val_has_pos_emb, attention_type=cfg.attention_type)
+            ca_val_has_pos_emb=cfg.ca_val_has_pos_emb, attention_type=cfg.attention_type,
+            attention_impl=cfg.get('attention_impl', 'fp32'))
         norm = nn.LayerNorm(cfg.d_embed) if cfg.pre_norm else None
         self.transformer_encoder = TransformerCrossEncoder(layer, cfg.num_encoder_layers, norm,
                                                            return_intermediate=True)

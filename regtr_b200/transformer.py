@@ -84,8 +84,11 @@ class AttentionPlan:
 class TransformerCrossEncoderLayer(nn.Module):
     def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu",
                  normalize_before=False, sa_val_has_pos_emb=False, ca_val_has_pos_emb=False,
-                 attention_type='dot_prod'):
+                 attention_type='dot_prod', attention_impl='fp32'):
         super().__init__()
+        if attention_impl not in ('fp32', 'bf16_tc'):
+            raise ValueError("attention_impl must be 'fp32' (parity) or 'bf16_tc' (tcgen05 tensor cores)")
+        self.attention_impl = attention_impl
         if attention_type != 'dot_prod':
             raise NotImplementedError
         if not normalize_before:
@@ -109,6 +112,10 @@ class TransformerCrossEncoderLayer(nn.Module):
     def _attend(self, mha: _MHAParams, x2, x2p, val_has_pos, plan: AttentionPlan, cross: bool):
         E = mha.embed_dim
         W, b = mha.in_proj_weight, mha.in_proj_bias
+        ks, kl = (plan.xk_start, plan.xk_len) if cross else (plan.q_start, plan.q_len)
+        if self.attention_impl == 'bf16_tc' and val_has_pos:
+            # fast mode: in-projection with a bf16 epilogue + tcgen05 attention core (TMA-fed, TMEM accumulators)
+            return ops.mha_bf16_tc(x2p, W, b, plan.q_start, plan.q_len, ks, kl, plan.max_len, self.nhead)
         if val_has_pos:
             qkv = ops.linear(x2p, W, b)                   # one packed in-projection GEMM
             q, k, v = qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:]
@@ -116,7 +123,6 @@ class TransformerCrossEncoderLayer(nn.Module):
             qk = ops.linear(x2p, W[:2 * E], b[:2 * E])
             q, k = qk[:, :E], qk[:, E:]
             v = ops.linear(x2, W[2 * E:], b[2 * E:])
-        ks, kl = (plan.xk_start, plan.xk_len) if cross else (plan.q_start, plan.q_len)
         o = ops.mha_varlen(q, k, v, plan.q_start, plan.q_len, ks, kl, plan.max_len, self.nhead)
         return o
 

@@ -300,3 +300,53 @@ def test_graphed_executor_matches_eager_and_survives_overflow():
     want, got = model(b_e), runner(b_g)
     assert runner.fallbacks == 1
     assert torch.equal(got['pose'], want['pose'])
+
+
+def test_tcgen05_attention_core_vs_fp32_kernel():
+    """bf16 tcgen05 attention (TMA-fed, TMEM accumulators) vs the fp32 parity kernel on ragged self and
+    cross problems (unaligned key ranges, partial tiles, a 7-token cloud).  Tolerance of the fast mode:
+    3e-2 * max|ref| (bf16 operands)."""
+    from regtr_b200 import ops
+    from regtr_b200.transformer import AttentionPlan
+    torch.manual_seed(0)
+    E, H = 256, 8
+    for lens in ([410, 339], [130, 7, 300, 129], [64, 64]):
+        N = sum(lens)
+        x = torch.randn(N, E, device=DEV)
+        W = torch.randn(3 * E, E, device=DEV) / E ** 0.5
+        b = torch.randn(3 * E, device=DEV) * 0.1
+        plan = AttentionPlan(lens, DEV)
+        qkv = ops.linear(x, W, b)
+        for ks, kl in ((plan.q_start, plan.q_len), (plan.xk_start, plan.xk_len)):
+            want = ops.mha_varlen(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], plan.q_start, plan.q_len, ks, kl,
+                                  plan.max_len, H)
+            got = ops.mha_bf16_tc(x, W, b, plan.q_start, plan.q_len, ks, kl, plan.max_len, H)
+            assert torch.isfinite(got).all()
+            assert float((got - want).abs().max()) <= 3e-2 * float(want.abs().max())
+
+
+def test_forward_fast_mode_bf16_attention():
+    """Full forward with attention_impl='bf16_tc' vs the oracle: indices exact (same pyramid), features
+    within 3e-2 * max|ref|, rotation still orthonormal; the parity mode keeps the 1e-4 pose bound."""
+    from oracle import pre, regtr_oracle as O
+    from regtr_b200.config import get_config
+    from regtr_b200.regtr import RegTR
+    from regtr_b200.synthetic import make_3dmatch_pair
+    from regtr_b200.weights import random_state_dict
+    cfg = get_config('3dmatch')
+    cfg.attention_impl = 'bf16_tc'
+    sd = random_state_dict(cfg, 5)
+    p = make_3dmatch_pair(2300, 6000)
+    model = RegTR(cfg).to(DEV).eval()
+    model.load_state_dict(sd, strict=True)
+    batch = {'src_xyz': [G(p['src_xyz'])], 'tgt_xyz': [G(p['tgt_xyz'])]}
+    out = model(batch)
+    want = pre.preprocess(cfg, [p['src_xyz'], p['tgt_xyz']])
+    ref = O.forward(sd, cfg, [p['src_xyz']], [p['tgt_xyz']], meta=want)
+    for k in ('src_feat', 'tgt_feat'):
+        a, b = N(out[k][0]), ref[k][0].numpy()
+        assert np.abs(a - b).max() <= 3e-2 * np.abs(b).max(), k
+    assert np.abs(N(out['src_feat_un'][0]) - ref['src_feat_un'][0].numpy()).max() <= 1e-4 * float(ref['src_feat_un'][0].abs().max())
+    R = N(out['pose'])[..., :3].astype(np.float64)
+    assert np.abs(R @ np.swapaxes(R, -1, -2) - np.eye(3)).max() <= 1e-5
+    assert np.abs(N(out['pose']) - ref['pose'].numpy()).max() <= 5e-2
