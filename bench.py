@@ -57,6 +57,8 @@ def parse():
     ap.add_argument('--checks', type=int, default=1, help='report pose error vs the oracle on one pair')
     ap.add_argument('--attention', default='fp32', choices=['fp32', 'bf16_tc'],
                     help="fp32: parity kernel (default, pose within 1e-4); bf16_tc: tcgen05 tensor-core core")
+    ap.add_argument('--inflight', type=int, default=2,
+                    help='independent pairs in flight per GPU (CUDA-graph executors on private streams); 1 = serial')
     ap.add_argument('--graph', type=int, default=1, help='1: CUDA-graph executor (GraphedRegTR); 0: eager forward')
     return ap.parse_args()
 
@@ -228,7 +230,7 @@ def main():
     from regtr_b200 import ops
     from regtr_b200.config import get_config
     from regtr_b200.dist import gather_poses
-    from regtr_b200.regtr import GraphedRegTR, RegTR
+    from regtr_b200.regtr import GraphedRegTR, PipelinedRegTR, RegTR
     from regtr_b200.weights import random_state_dict
 
     assert torch.cuda.is_available(), 'bench.py --impl b200 needs a CUDA device (no CPU fallback)'
@@ -247,6 +249,8 @@ def main():
     model = RegTR(cfg).to(dev).eval()
     model.load_state_dict(sd, strict=True)
     runner = GraphedRegTR(model) if args.graph else model      # the public call a user makes
+    depth = args.inflight if args.graph else 1
+    pipe = PipelinedRegTR(model, depth) if depth > 1 else None
 
     # rank-local pool of distinct pairs (generated rank-locally)
     n_pool = max(POOL, B)
@@ -283,42 +287,74 @@ def main():
     # ---------------- warm-up
     for i in range(W):
         device_step(i)
+    if pipe is not None:
+        for i in range(2 * depth):
+            pipe.submit(batch_at(i, resident)[0])
+        pipe.drain()
     barrier()
+
+    def run_pipelined(src):
+        """K steps with `depth` forwards in flight; returns (elapsed ms on the device, bytes in/out)."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        outs = []
+        for i in range(K):
+            done = pipe.submit(batch_at(W + i, src)[0], pre_hook=flush.zero_)
+            if done is not None:
+                outs.append(done['pose_host'].clone())
+        outs += [o['pose_host'].clone() for o in pipe.drain()]
+        pipe.join()
+        if world > 1:                           # the run's poses, gathered over the ranks (288 B / pair)
+            gather_poses(torch.cat(outs, dim=1).to(dev, non_blocking=True), B * K * world)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), outs
 
     # ---------------- timed region: K steps, HBM-resident inputs
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = ops.LAUNCHES
-    evs = []
     barrier()
-    for i in range(K):
-        flush.zero_()                                   # L2 flush between timed steps (not timed)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        device_step(W + i)
-        e1.record()
-        evs.append((e0, e1))
-    barrier()
+    if pipe is None:
+        evs = []
+        for i in range(K):
+            flush.zero_()                                   # L2 flush between timed steps (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            device_step(W + i)
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        t_dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    else:
+        t_dev_ms, _ = run_pipelined(resident)               # includes the per-step L2 flush kernels
+        barrier()
     launches = ops.LAUNCHES - launches0
-    t_dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     log(f'device-resident: {t_dev_ms / K:.3f} ms/step')
 
     # ---------------- end-to-end: host buffers in, pose on the host out
-    for i in range(2):
-        e2e_step(i)
-    barrier()
-    evs = []
-    h2d = d2h = 0
-    for i in range(K):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        pose_h, ids = e2e_step(W + i)
-        e1.record()
-        evs.append((e0, e1))
-        h2d = sum(host[j][0].numel() * 4 + host[j][1].numel() * 4 for j in ids)
-        d2h = pose_h.numel() * 4
-    barrier()
-    t_e2e_ms = sum(a.elapsed_time(b) for a, b in evs)
+    h2d = sum(host[j][0].numel() * 4 + host[j][1].numel() * 4 for j in batch_at(W, host)[1])
+    if pipe is None:
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        evs = []
+        d2h = 0
+        for i in range(K):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pose_h, ids = e2e_step(W + i)
+            e1.record()
+            evs.append((e0, e1))
+            d2h = pose_h.numel() * 4
+        barrier()
+        t_e2e_ms = sum(a.elapsed_time(b) for a, b in evs)
+    else:
+        run_pipelined(host)
+        barrier()
+        t_e2e_ms, outs = run_pipelined(host)
+        d2h = outs[-1].numel() * 4
+        barrier()
     clocks = sampler.stop() if sampler else None
     log(f'e2e: {t_e2e_ms / K:.3f} ms/step; clocks {clocks}')
 
@@ -398,7 +434,10 @@ def main():
                         parallelism=f'pair-level data parallel x{world}', l2_flush_between_steps=True,
                         weights='seeded random init (no pretrained weights offline)', precision_mode='fp32 parity (3xTF32 tcgen05 GEMMs, fp32 attention)' if args.attention == 'fp32'
                         else 'fast (3xTF32 GEMMs, bf16 tcgen05 attention core)',
-                        executor='cuda-graph (GraphedRegTR)' if args.graph else 'eager'),
+                        executor=(f'cuda-graph, {depth} pairs in flight (PipelinedRegTR)' if depth > 1 else
+                                  'cuda-graph (GraphedRegTR)') if args.graph else 'eager',
+                        timed_region='K steps incl. one 256 MB L2-flush kernel per step' if depth > 1 else
+                                     'per-step CUDA events, L2 flush between steps not timed'),
             e2e=dict(value=pairs / (t_e2e_ms * 1e-3), unit='pairs/s', h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h, ms_per_step=t_e2e_ms / K),
             gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu,

@@ -243,6 +243,27 @@ __global__ void k_max_pool_scalar(const float* __restrict__ x, const int32_t* __
     out[(size_t)qi * C + c] = m;
 }
 
+// out[n, o] = sum_k a[n, k] * W[k, o] for a tiny K (the first block: K = 15 * in_feats_dim = 15, which
+// breaks the 16-byte TMA pitch of the tensor-core GEMM).  One thread per 4 outputs, W in smem.
+__global__ void k_gemm_smallk(const float* __restrict__ a, const float* __restrict__ W, int n, int K, int Cout,
+                              const int32_t* __restrict__ n_dev, float* __restrict__ out) {
+    extern __shared__ float w_s[];
+    for (int t = threadIdx.x; t < K * Cout; t += blockDim.x) w_s[t] = W[t];
+    __syncthreads();
+    if (n_dev) n = min(n, *n_dev);
+    const int c4 = Cout >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n * c4) return;
+    const int r = (int)(t / c4), c = (int)(t % c4) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < K; ++k) {
+        const float av = a[(size_t)r * K + k];
+        const float4 wv = *reinterpret_cast<const float4*>(w_s + k * Cout + c);
+        acc.x = fmaf(av, wv.x, acc.x); acc.y = fmaf(av, wv.y, acc.y); acc.z = fmaf(av, wv.z, acc.z); acc.w = fmaf(av, wv.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(out + (size_t)r * Cout + c) = acc;
+}
+
 // ---- cuBLAS handle (one per device, created on first use)
 std::mutex g_mu;
 cublasHandle_t g_handles[64] = {};
@@ -331,7 +352,15 @@ int regtr_kpconv_fwd(const float* q, const float* s, const int32_t* idx, const f
     uint8_t* flags = (uint8_t*)ws + regtr_align(sizeof(float) * (size_t)Nq * KP * (size_t)Cin);
     int rc = regtr_kpconv_aggregate(q, s, idx, x, kp, Nq, Ns, nq_dev, ns_dev, K, Cin, extent, wf, flags, stream_);
     if (rc != REGTR_OK) return rc;
+    const int KDs = KP * Cin;
+    if (KDs <= 64 && Cout % 4 == 0 && (size_t)KDs * Cout * sizeof(float) <= 48 * 1024) {
+        k_gemm_smallk<<<regtr_cdiv((long long)Nq * (Cout / 4), 256), 256, (size_t)KDs * Cout * sizeof(float), st>>>(
+            wf, W, Nq, KDs, Cout, nq_dev, out);
+        REGTR_CHECK_LAUNCH();
+        return REGTR_OK;
+    }
     // out[Nq,Cout] = wf[Nq,15*Cin] @ W[15*Cin,Cout]  (row-major)  ==  column-major out^T = W^T wf^T
+    // (library fallback of the C entry point; the Python path runs this contraction on k_gemm_tf32x3)
     cublasHandle_t h = get_handle();
     if (!h) return REGTR_ERR_CUBLAS;
     if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) return REGTR_ERR_CUBLAS;

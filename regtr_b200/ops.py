@@ -46,9 +46,15 @@ def _chk(t, dtype, name, dims=None):
     return t
 
 
+# Scratch buffers are shared by every call on a stream.  Executors that may run CONCURRENTLY on
+# different streams (pipelined CUDA graphs) set a private namespace while they capture, so that the
+# pointers baked into their graphs never alias another executor's scratch.
+WS_NAMESPACE = None
+
+
 def workspace(nbytes: int, device, slot: str = 'default') -> torch.Tensor:
-    """Per-(device, slot) grow-only scratch buffer (stream-ordered reuse)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+    """Per-(device, namespace, slot) grow-only scratch buffer (stream-ordered reuse)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), WS_NAMESPACE, slot)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=device)

@@ -161,6 +161,13 @@ class GraphedRegTR:
         self.fallbacks = 0
 
     def _capture(self, B: int, cap0: int):
+        prev_ns, ops.WS_NAMESPACE = ops.WS_NAMESPACE, id(self)       # private scratch for this executor's graphs
+        try:
+            return self._capture_impl(B, cap0)
+        finally:
+            ops.WS_NAMESPACE = prev_ns
+
+    def _capture_impl(self, B: int, cap0: int):
         from .kpconv import level_capacities
         model = self.model
         dev = model.device
@@ -187,16 +194,22 @@ class GraphedRegTR:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         g = torch.cuda.CUDAGraph()
+        n0 = ops.LAUNCHES
         with torch.cuda.graph(g):
             pyr, core, tail = run()
+        st['n_launches'] = ops.LAUNCHES - n0       # hand-written kernels per replay (for launch accounting)
         st.update(graph=g, pyr=pyr, core=core, tail=tail,
                   tail_host=torch.empty(tail.numel(), dtype=torch.int32).pin_memory(),
                   pose_host=torch.empty(tuple(core['pose'].shape), dtype=torch.float32).pin_memory(),
-                  stage=torch.empty((cap0, 3), dtype=torch.float32).pin_memory())
+                  offs_host=torch.empty(2 * B + 1, dtype=torch.int32).pin_memory(),
+                  done=torch.cuda.Event())
         return st
 
     @torch.no_grad()
-    def __call__(self, batch):
+    def submit(self, batch):
+        """Enqueue one forward on the current stream (no host synchronisation): copy the clouds into the
+        static buffers, replay the graph, start the D2H of (level sizes, status, pose).  Returns a ticket
+        for `result`."""
         model = self.model
         dev = model.device
         src, tgt = list(batch['src_xyz']), list(batch['tgt_xyz'])
@@ -209,7 +222,6 @@ class GraphedRegTR:
         st = self.graphs.get(key)
         if st is None:
             st = self.graphs[key] = self._capture(B, cap0)
-        # ---- inputs -> static buffers (one packed copy)
         offs = [0]
         for v in lens0:
             offs.append(offs[-1] + v)
@@ -218,12 +230,22 @@ class GraphedRegTR:
         else:                                   # host clouds: asynchronous H2D straight into the packed buffer
             for c, a in zip(clouds, offs):      # (pinned sources copy without a staging pass)
                 st['points'][a:a + c.shape[0]].copy_(c, non_blocking=True)
-        st['offs0'].copy_(torch.tensor(offs, dtype=torch.int32), non_blocking=True)
-        # ---- replay + the single D2H / sync
+        st['offs_host'].copy_(torch.tensor(offs, dtype=torch.int32))
+        st['offs0'].copy_(st['offs_host'], non_blocking=True)
         st['graph'].replay()
+        ops.LAUNCHES += st['n_launches']
         st['tail_host'].copy_(st['tail'], non_blocking=True)
         st['pose_host'].copy_(st['core']['pose'], non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        st['done'].record(torch.cuda.current_stream(dev))
+        return (key, st, batch, B)
+
+    @torch.no_grad()
+    def result(self, ticket):
+        """Wait for a submitted forward and assemble the reference's output dict (views into the graph's
+        static buffers: valid until the next submit on the same capacity bucket)."""
+        key, st, batch, B = ticket
+        model = self.model
+        st['done'].synchronize()
         pyr = st['pyr']
         n_lvl = len(pyr.levels)
         host = st['tail_host']
@@ -232,7 +254,7 @@ class GraphedRegTR:
             self.fallbacks += 1                 # re-capture this bucket with more head-room next time
             if self.ratios.get(key, self.ratio) < self.retry_ratio:
                 self.ratios[key] = self.retry_ratio
-                del self.graphs[key]
+                self.graphs.pop(key, None)
             return model.forward(batch)
         offs_host = host[:-1].reshape(n_lvl, 2 * B + 1)
         meta = model.preprocessor.finalize(pyr, host=(offs_host, code))
@@ -240,3 +262,49 @@ class GraphedRegTR:
         out = model._assemble(st['core'], meta['_lens'][-1], B)
         out['pose_host'] = st['pose_host']
         return out
+
+    def __call__(self, batch):
+        return self.result(self.submit(batch))
+
+
+class PipelinedRegTR:
+    """`depth` CUDA-graph executors on private streams, used round-robin: while the GPU finishes pair i,
+    pairs i+1 .. i+depth-1 are already enqueued, so the many small latency-bound kernels of one forward
+    overlap with another pair's (independent pairs; SURVEY.md 8e).  `submit` returns immediately;
+    `result` of the oldest ticket is taken when its slot is needed again or on `drain`."""
+
+    def __init__(self, model: RegTR, depth: int = 2, **kw):
+        self.slots = [GraphedRegTR(model, **kw) for _ in range(depth)]
+        self.streams = [torch.cuda.Stream(device=model.device) for _ in range(depth)]
+        self.pending = [None] * depth
+        self.i = 0
+
+    def submit(self, batch, pre_hook=None):
+        """Returns the finished output of the forward that previously used this slot (or None).
+        `pre_hook()` (e.g. a benchmark's L2 flush) runs on the slot's stream right before the forward."""
+        k = self.i % len(self.slots)
+        self.i += 1
+        done = None
+        if self.pending[k] is not None:
+            done = self.slots[k].result(self.pending[k])
+        self.streams[k].wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.streams[k]):
+            if pre_hook is not None:
+                pre_hook()
+            self.pending[k] = self.slots[k].submit(batch)
+        return done
+
+    def join(self):
+        """Make the current stream wait for every slot stream (for event timing on the current stream)."""
+        for st in self.streams:
+            torch.cuda.current_stream().wait_stream(st)
+
+    def drain(self):
+        outs = []
+        n = len(self.slots)
+        for j in range(n):
+            k = (self.i + j) % n
+            if self.pending[k] is not None:
+                outs.append(self.slots[k].result(self.pending[k]))
+                self.pending[k] = None
+        return outs
