@@ -57,7 +57,7 @@ def parse():
     ap.add_argument('--checks', type=int, default=1, help='report pose error vs the oracle on one pair')
     ap.add_argument('--attention', default='fp32', choices=['fp32', 'bf16_tc'],
                     help="fp32: parity kernel (default, pose within 1e-4); bf16_tc: tcgen05 tensor-core core")
-    ap.add_argument('--inflight', type=int, default=2,
+    ap.add_argument('--inflight', type=int, default=6,
                     help='independent pairs in flight per GPU (CUDA-graph executors on private streams); 1 = serial')
     ap.add_argument('--graph', type=int, default=1, help='1: CUDA-graph executor (GraphedRegTR); 0: eager forward')
     return ap.parse_args()
@@ -287,9 +287,10 @@ def main():
     # ---------------- warm-up
     for i in range(W):
         device_step(i)
-    if pipe is not None:
+    if pipe is not None:                        # capture every (slot, capacity bucket) graph before timing
+        pipe.warm([batch_at(i, resident)[0] for i in range(-(-n_pool // B))])
         for i in range(2 * depth):
-            pipe.submit(batch_at(i, resident)[0])
+            pipe.submit(batch_at(i, host)[0])
         pipe.drain()
     barrier()
 

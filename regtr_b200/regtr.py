@@ -294,6 +294,14 @@ class PipelinedRegTR:
             self.pending[k] = self.slots[k].submit(batch)
         return done
 
+    def warm(self, batches):
+        """Capture every (slot, capacity bucket) graph needed by `batches` ahead of time."""
+        for k, slot in enumerate(self.slots):
+            with torch.cuda.stream(self.streams[k]):
+                for b in batches:
+                    slot(dict(b))
+        torch.cuda.synchronize()
+
     def join(self):
         """Make the current stream wait for every slot stream (for event timing on the current stream)."""
         for st in self.streams:
