@@ -48,7 +48,7 @@ def cpu_threads():
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--config', type=int, default=2, help='BASELINE.json config id (2..5)')
@@ -102,7 +102,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """Start of the window whose samples are reported (the timed region)."""
+        self.t0 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -114,7 +118,9 @@ class ClockSampler:
             pass
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        t0 = getattr(self, 't0', 0.0)
+        rows = [r for t, r in self.rows if t >= t0] or [r for _, r in self.rows[-3:]]
+        for r in rows:
             f = [x.strip() for x in r.split(',')]
             if len(f) < 7:
                 continue
@@ -283,6 +289,7 @@ def main():
             return gather_poses(out['pose'], B * world).cpu(), ids
         return (out['pose_host'] if 'pose_host' in out else out['pose'].cpu()), ids
 
+    sampler = ClockSampler(local) if rank == 0 else None     # started early: nvidia-smi needs ~0.1 s to report
     log(f'pool ready ({n_pool} pairs, {sum(len(a) + len(b) for a, b in pool) // n_pool} pts/pair); warm-up')
     # ---------------- warm-up
     for i in range(W):
@@ -312,7 +319,8 @@ def main():
         return e0.elapsed_time(e1), outs
 
     # ---------------- timed region: K steps, HBM-resident inputs
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     launches0 = ops.LAUNCHES
     barrier()
     if pipe is None:
