@@ -61,18 +61,25 @@ __device__ __forceinline__ void stage_neighbours(const float* __restrict__ s, co
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, o);
+    // pad the neighbour list to a multiple of 4 with copies of a valid id and ZERO influences, so that
+    // the aggregation loop needs no bounds predicates
+    const int padded = (base + 3) & ~3;
+    if (lane < padded - base) { id_s[base + lane] = base > 0 ? id_s[0] : 0; rel_s[base + lane] = make_float4(0.f, 0.f, 0.f, 0.f); }
     __syncwarp();
-    for (int t = lane; t < base * KPP; t += 32) {
-        const int k = t >> 4, p = t & 15;
+    // lane -> fixed kernel point p = lane & 15 (held in registers), neighbours k = (lane >> 4) + 2 r
+    const int p = lane & 15;
+    const bool real = p < KP;
+    const float kx = real ? kp_s[3 * p + 0] : 0.f, ky = real ? kp_s[3 * p + 1] : 0.f, kz = real ? kp_s[3 * p + 2] : 0.f;
+    for (int k = lane >> 4; k < padded; k += 2) {
         float w = 0.f;
-        if (p < KP) {
+        if (real && k < base) {
             const float4 r = rel_s[k];
-            const float dx = r.x - kp_s[3 * p + 0], dy = r.y - kp_s[3 * p + 1], dz = r.z - kp_s[3 * p + 2];
+            const float dx = r.x - kx, dy = r.y - ky, dz = r.z - kz;
             const float d2 = dx * dx + dy * dy + dz * dz;
             const float d = d2 > 0.f ? d2 * rsqrtf(d2) : 0.f;          // |.|: <= 2 ulp, far inside the tolerance
             w = fmaxf(0.f, 1.f - d * inv_extent);
         }
-        w_s[t] = w;
+        w_s[k * KPP + p] = w;
     }
     __syncwarp();
     n_valid = base;
@@ -117,12 +124,12 @@ k_kpconv_agg(const float* __restrict__ q, const float* __restrict__ s, const int
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[j][v] = 0ull;
 
-    for (int k0 = 0; k0 < n_valid; k0 += UNROLL) {
+    const int n_pad = (n_valid + 3) & ~3;          // UNROLL divides 4; padded slots carry zero influences
+    for (int k0 = 0; k0 < n_pad; k0 += UNROLL) {
         float xv[UNROLL][VEC];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const int kk = min(k0 + u, n_valid - 1);
-            const float* row = x + (size_t)id_s[kk] * CIN;
+            const float* row = x + (size_t)id_s[k0 + u] * CIN;
             if constexpr (VEC == 1) {
                 xv[u][0] = __ldg(row + lane);
             } else if constexpr (VEC == 2) {
@@ -138,16 +145,14 @@ k_kpconv_agg(const float* __restrict__ q, const float* __restrict__ s, const int
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            if (k0 + u < n_valid) {
-                const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(w_s + (k0 + u) * KPP);
-                const ulonglong2 a = wr[0], b = wr[1], c = wr[2], d = wr[3];
-                const f2 w2[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+            const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(w_s + (k0 + u) * KPP);
+            const ulonglong2 a = wr[0], b = wr[1], c = wr[2], d = wr[3];
+            const f2 w2[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    const f2 xx = f2_dup(xv[u][v]);
+            for (int v = 0; v < VEC; ++v) {
+                const f2 xx = f2_dup(xv[u][v]);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[j][v] = f2_fma(w2[j], xx, acc[j][v]);
-                }
+                for (int j = 0; j < 8; ++j) acc[j][v] = f2_fma(w2[j], xx, acc[j][v]);
             }
         }
     }
