@@ -399,8 +399,16 @@ int regtr_gemm_tf32x3_qkv_bf16(const float* A, int lda, const float* B_hi, const
         return REGTR_ERR_UNSUPPORTED;
     QkvOut q{(__nv_bfloat16*)qk_out, ld_qk, (__nv_bfloat16*)vt_out, ld_vt, split};
     float* dummy = reinterpret_cast<float*>(qk_out);      // C is never written in this mode
-    if (K <= 128) return launch_gemm<32, 2>(A, lda, B_hi, B_lo, ldb, dummy, 0, bias, nullptr, 0, M, N, K, m_dev, 0, 1, nullptr, st, q);
-    return launch_gemm<32, 4>(A, lda, B_hi, B_lo, ldb, dummy, 0, bias, nullptr, 0, M, N, K, m_dev, 0, 1, nullptr, st, q);
+    const int bn = choose_bn(M, N);
+    const bool shortk = K <= 128;
+#define REGTR_QKV_CASE(BN_, ST_)                                                                                  \
+    return launch_gemm<BN_, ST_>(A, lda, B_hi, B_lo, ldb, dummy, 0, bias, nullptr, 0, M, N, K, m_dev, 0, 1, nullptr, \
+                                 st, q)
+    if (bn == 128) { if (shortk) REGTR_QKV_CASE(128, 2); REGTR_QKV_CASE(128, 3); }
+    if (bn == 64) { if (shortk) REGTR_QKV_CASE(64, 2); REGTR_QKV_CASE(64, 4); }
+    if (shortk) REGTR_QKV_CASE(32, 2);
+    REGTR_QKV_CASE(32, 4);
+#undef REGTR_QKV_CASE
 }
 
 }  // extern "C"
