@@ -306,10 +306,13 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         outs = []
+        t_cpu = time.perf_counter()
         for i in range(K):
             done = pipe.submit(batch_at(W + i, src)[0], pre_hook=flush.zero_)
             if done is not None:
                 outs.append(done['pose_host'].clone())
+        t_cpu = time.perf_counter() - t_cpu
+        log(f'host time in submit/result: {1e3 * t_cpu / K:.3f} ms/step')
         outs += [o['pose_host'].clone() for o in pipe.drain()]
         pipe.join()
         if world > 1:                           # the run's poses, gathered over the ranks (288 B / pair)
