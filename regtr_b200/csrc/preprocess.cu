@@ -173,16 +173,19 @@ k_ball_query(const float* __restrict__ q, const int32_t* __restrict__ q_offs, co
     const float r2 = __fmul_rn(radius, radius);
     const int seg_lo = s_offs[c], seg_hi = s_offs[c + 1];
 
-    // lanes 0..8: one (dx,dy) column of three z-adjacent cells = one contiguous key range
-    int lo = 0, hi = 0;
-    if (lane < 9) {
-        const int x = cx + lane / 3 - 1, y = cy + lane % 3 - 1;
+    // 9 (dx,dy) columns of three z-adjacent cells = 9 contiguous key ranges; lane r searches the lower
+    // bound of range r, lane 9+r its upper bound (18 independent binary searches in parallel)
+    int bound = 0;
+    if (lane < 18) {
+        const int r = lane < 9 ? lane : lane - 9;
+        const int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
         if (x >= -32767 && x <= 32767 && y >= -32767 && y <= 32767 && cz >= -32767 && cz <= 32766) {
-            const int z0 = cz - 1, z1 = cz + 1;
-            lo = lower_bound_u64(skeys, seg_lo, seg_hi, regtr_pack_key(c, x, y, z0));
-            hi = lower_bound_u64(skeys, lo, seg_hi, regtr_pack_key(c, x, y, z1) + 1ull);
+            const unsigned long long key = lane < 9 ? regtr_pack_key(c, x, y, cz - 1) : regtr_pack_key(c, x, y, cz + 1) + 1ull;
+            bound = lower_bound_u64(skeys, seg_lo, seg_hi, key);
         }
     }
+    const int lo = bound;
+    const int hi = __shfl_sync(0xffffffffu, bound, (lane + 9) & 31);   // lanes 0..8: their range's upper bound
     int* hits = s_hits[warp];
     int* sel = s_sel[warp];
     int count = 0;
