@@ -18,6 +18,8 @@
 // B (weights) is split once on the host side of the ABI (regtr_split_tf32) and cached.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -47,7 +49,7 @@ template <int BN, int ST> struct Cfg {
     // accumulations drifts (measured: error grows ~linearly with K).  The k-steps of a k-block
     // are therefore spread over NACC independent TMEM accumulators that are summed with
     // round-to-nearest fp32 adds in the epilogue (4x fewer hardware accumulations each).
-    static constexpr int NACC = (BN == 128 && ST == 2) ? 2 : 4;   // 2 CTAs/SM must share 512 columns
+    static constexpr int NACC = (BN == 256 || (BN == 128 && ST == 2)) ? 2 : 4;   // co-resident CTAs share 512 columns
     static constexpr int TMEM_COLS = NACC * BN;
 };
 
@@ -267,11 +269,12 @@ int choose_splits(int M, int N, int K, int bn) {
     return s < 1 ? 1 : s;
 }
 
+// Widest tile that covers N: the pipeline keeps several independent pairs in flight, so the machine is
+// filled by OTHER forwards and what counts is the total CTA time (A is streamed / split once per
+// N-tile): measured 632 -> 696 pairs/s against a "fill 148 SMs per launch" heuristic.
 int choose_bn(int M, int N) {
-    const int mt = regtr_cdiv(M, BM);
-    if (N <= 32) return 32;
-    if (N <= 64) return mt >= 148 ? 64 : 32;
-    return mt * regtr_cdiv(N, 128) >= 148 ? 128 : (mt * regtr_cdiv(N, 64) >= 148 ? 64 : 32);
+    (void)M;
+    return N > 64 ? 128 : (N > 32 ? 64 : 32);
 }
 
 // ---- host: tensor maps (driver entry point resolved through the runtime, no libcuda link)
@@ -378,10 +381,16 @@ int regtr_gemm_tf32x3(const float* A, int lda, const float* B_hi, const float* B
 #define REGTR_GEMM_CASE(BN_, ST_)                                                                              \
     return launch_gemm<BN_, ST_>(A, lda, B_hi, B_lo, ldb, C, ldc, bias, R, ldr, M, N, K, m_dev, relu, splits, \
                                  (float*)ws, st)
-    if (bn == 128) { if (shortk) REGTR_GEMM_CASE(128, 2); REGTR_GEMM_CASE(128, 3); }
-    if (bn == 64) { if (shortk) REGTR_GEMM_CASE(64, 2); REGTR_GEMM_CASE(64, 4); }
-    if (shortk) REGTR_GEMM_CASE(32, 2);
-    REGTR_GEMM_CASE(32, 4);
+    // 2-stage variants keep the CTA under half an SM's shared memory (2 CTAs/SM): latency is hidden by
+    // the co-resident CTA instead of a deeper pipeline (measured: GEMMs were 43 % of the pair time with
+    // 1 CTA/SM because a resident CTA mostly waits and blocks other pairs' CTAs from the SM)
+    // Small grids (<= one CTA per SM) are latency-critical: 4 stages put the whole K run in flight at once.
+    (void)shortk;
+    const bool small_grid = false;   // measured: deeper pipelines for small grids lose 2 % under 6-way overlap
+    if (bn == 128) { if (K <= 128) REGTR_GEMM_CASE(128, 2); REGTR_GEMM_CASE(128, 3); }
+    if (bn == 64) { if (small_grid) REGTR_GEMM_CASE(64, 4); REGTR_GEMM_CASE(64, 2); }
+    if (small_grid) REGTR_GEMM_CASE(32, 4);
+    REGTR_GEMM_CASE(32, 2);
 #undef REGTR_GEMM_CASE
 }
 
@@ -404,10 +413,10 @@ int regtr_gemm_tf32x3_qkv_bf16(const float* A, int lda, const float* B_hi, const
 #define REGTR_QKV_CASE(BN_, ST_)                                                                                  \
     return launch_gemm<BN_, ST_>(A, lda, B_hi, B_lo, ldb, dummy, 0, bias, nullptr, 0, M, N, K, m_dev, 0, 1, nullptr, \
                                  st, q)
-    if (bn == 128) { if (shortk) REGTR_QKV_CASE(128, 2); REGTR_QKV_CASE(128, 3); }
-    if (bn == 64) { if (shortk) REGTR_QKV_CASE(64, 2); REGTR_QKV_CASE(64, 4); }
-    if (shortk) REGTR_QKV_CASE(32, 2);
-    REGTR_QKV_CASE(32, 4);
+    (void)shortk;
+    if (bn == 128) { if (K <= 128) REGTR_QKV_CASE(128, 2); REGTR_QKV_CASE(128, 3); }
+    if (bn == 64) REGTR_QKV_CASE(64, 2);
+    REGTR_QKV_CASE(32, 2);
 #undef REGTR_QKV_CASE
 }
 

@@ -115,7 +115,7 @@ class PreprocessorGPU(nn.Module):
                 p32, p64 = ops.ball_query(nxt, offs_all[li + 1], cur, offs, grid, K, r, want64=want64)
                 nxt_grid = ops.CellGrid(nxt, offs_all[li + 1], n_clouds, 2 * r * _CELL_SLACK, status)
                 u64 = None
-                if self.compute_upsamples and want64:
+                if self.compute_upsamples and want64 and 'bq_up' not in ops._ABLATE:
                     _, u64 = ops.ball_query(cur, offs, nxt, offs_all[li + 1], nxt_grid, K, 2 * r,
                                             q_order=grid.order, want32=False)
                 pool32.append(p32); pool64.append(p64); up64.append(u64)

@@ -14,6 +14,11 @@ from . import lib as _lib
 
 _ws_cache = {}
 
+# Diagnosis only (scripts/ablate.sh): REGTR_ABLATE=mha,agg,... skips a stage to measure its marginal cost
+# under multi-stream overlap.  Never set in tests or in the benchmark.
+import os as _os
+_ABLATE = set(filter(None, _os.environ.get('REGTR_ABLATE', '').split(',')))
+
 # Number of hand-written kernels (libregtr_b200.so, excluding CUB / cuBLAS) launched so far.
 LAUNCHES = 0
 # Optional profiler: when set to a list, ops.kpconv appends (cuda start event, end event, info dict)
@@ -164,7 +169,8 @@ def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=No
         # gather/aggregate kernel, then the [Nq,15Cin] x [15Cin,Cout] contraction on the tensor cores
         wf = ws[:Nq * 15 * Cin * 4].view(torch.float32).view(Nq, 15 * Cin)
         flags = ws[regtr_align_up(Nq * 15 * Cin * 4):]
-        _lib.check(L.regtr_kpconv_aggregate(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(kernel_points), Nq, Ns,
+        if 'agg' not in _ABLATE:
+          _lib.check(L.regtr_kpconv_aggregate(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(kernel_points), Nq, Ns,
                                             _p(nq_dev), _p(ns_dev), K, Cin, float(extent), _p(wf), _p(flags),
                                             _stream()), 'regtr_kpconv_aggregate')
         _count(2)
@@ -219,6 +225,8 @@ def instnorm_act(x, offs, n_clouds: int, res=None, slope: float = -1.0, eps: flo
     if res is not None:
         _chk(res, torch.float32, 'res', 2)
     out = torch.empty_like(x) if out is None else out
+    if 'norm' in _ABLATE:
+        return out.copy_(x)
     nb = L.regtr_instnorm_ws_bytes(n, n_clouds, C)
     ws = workspace(nb, x.device, 'instnorm')
     _lib.check(L.regtr_instnorm_act(_p(x), _p(offs), n_clouds, n, C, float(eps), _p(res), float(slope), _p(out),
@@ -258,6 +266,8 @@ def gemm(a, b_hi, b_lo, bias=None, residual=None, relu=False, m_dev=None, out=No
     M, K = a.shape
     N = b_hi.shape[0]
     out = torch.empty((M, N), dtype=torch.float32, device=a.device) if out is None else out
+    if 'gemm' in _ABLATE:
+        return out.zero_()
     nb = L.regtr_gemm_ws_bytes(M, N, K)
     ws = workspace(nb, a.device, 'gemm')
     _lib.check(L.regtr_gemm_tf32x3(_p(a), a.stride(0), _p(b_hi), _p(b_lo), b_hi.stride(0), _p(out), out.stride(0),
@@ -323,6 +333,8 @@ def layernorm_pos(x, gamma, beta, pos=None, eps: float = 1e-5, want_plain=True, 
     n, E = x.shape
     y = torch.empty_like(x) if want_plain else None
     yp = torch.empty_like(x) if want_pos else None
+    if 'ln' in _ABLATE:
+        return (y.copy_(x) if y is not None else None), (yp.copy_(x) if yp is not None else None)
     _lib.check(L.regtr_layernorm_pos(_p(x), _p(gamma), _p(beta), _p(pos), n, E, float(eps), _p(y), _p(yp), _stream()),
                'regtr_layernorm_pos')
     _count(1)
@@ -350,6 +362,8 @@ def mha_varlen(q, k, v, q_start, q_len, k_start, k_len, max_q_len: int, n_heads:
     dh = E // n_heads
     # zeros: rows outside every problem (capacity padding) stay finite for the GEMMs downstream
     out = torch.zeros((q.shape[0], E), dtype=torch.float32, device=q.device) if out is None else out
+    if 'mha' in _ABLATE:
+        return out
     _lib.check(L.regtr_mha_varlen_fwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
                                       out.stride(0), _p(q_start), _p(q_len), _p(k_start), _p(k_len),
                                       q_start.numel(), int(max_q_len), n_heads, dh, 1.0 / math.sqrt(dh), _stream()),
