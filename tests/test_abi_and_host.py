@@ -108,3 +108,30 @@ def test_gather_poses_world2_gloo():
                      for l in range(6)])
     for r in range(world):
         assert np.array_equal(res[r], want)
+
+
+def test_level_capacities_are_monotone_and_roomy():
+    from regtr_b200.config import get_config
+    from regtr_b200.kpconv import level_capacities
+    cfg = get_config('3dmatch')
+    for cap0 in (8192, 40960, 327680):
+        caps = level_capacities(cfg, cap0, ratio=0.30)
+        assert len(caps) == 4 and caps[0] == cap0
+        assert all(a >= b for a, b in zip(caps, caps[1:]))
+        assert all(c % 256 == 0 for c in caps[1:])
+        # real 3DMatch keeps 26-27 % of the points per level (38061 -> 10088 -> 2753 -> 751)
+        assert caps[1] >= 0.27 * cap0 and caps[3] >= 0.27 ** 3 * cap0
+    assert level_capacities(get_config('modelnet'), 8192)[1] <= 8192
+
+
+def test_header_and_binding_signatures_agree_in_arity():
+    """Every C prototype in include/regtr_b200.h has as many parameters as its ctypes signature."""
+    import re
+    from regtr_b200 import lib
+    text = re.sub(r'/\*.*?\*/', '', open(lib.HEADER).read(), flags=re.S)
+    for name, (_, args) in lib.SIGNATURES.items():
+        m = re.search(r'\b' + name + r'\s*\(([^;]*?)\)\s*;', text, flags=re.S)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ('', 'void') else params.count(',') + 1
+        assert n == len(args), f'{name}: header has {n} parameters, binding has {len(args)}'
