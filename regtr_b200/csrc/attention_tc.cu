@@ -17,8 +17,6 @@
 // S is double buffered in TMEM so that Q K^T of tile i+1 overlaps the softmax of tile i.
 #include <cuda_bf16.h>
 
-#include <cstdlib>
-
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -50,7 +48,7 @@ __global__ void __launch_bounds__(192, 2)
 k_mha_bf16_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmVt, float* __restrict__ O, int ldo, int E,
               const int32_t* __restrict__ q_start, const int32_t* __restrict__ q_len,
-              const int32_t* __restrict__ k_start, const int32_t* __restrict__ k_len, float scale_log2e, int dbg) {
+              const int32_t* __restrict__ k_start, const int32_t* __restrict__ k_len, float scale_log2e) {
     extern __shared__ unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int prob = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
@@ -134,7 +132,7 @@ k_mha_bf16_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 const uint64_t dK = umma_desc_sw64_kmajor(tc::smem_u32(sK(s)));
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k)              // UMMA_K = 16 bf16 = 32 bytes
-                    if (!(dbg & 2)) tc::umma_f16(tmem + (uint32_t)(s * BKEY), dQ + (uint64_t)(k * 2), dK + (uint64_t)(k * 2), idesc_s, k != 0);
+                    tc::umma_f16(tmem + (uint32_t)(s * BKEY), dQ + (uint64_t)(k * 2), dK + (uint64_t)(k * 2), idesc_s, k != 0);
                 tc::umma_commit(&s_full[s]);
                 if (it < n_kt) tc::umma_commit(&kv_empty[s]);   // pass 1: the stage is free once QK^T retired
             };
@@ -151,7 +149,7 @@ k_mha_bf16_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                     const uint64_t dV = tc::umma_desc_sw128_kmajor(tc::smem_u32(sV(s)));
 #pragma unroll
                     for (int k = 0; k < BKEY / 16; ++k)
-                        if (!(dbg & 1)) tc::umma_f16(tmem_O, dP + (uint64_t)(k * 2), dV + (uint64_t)(k * 2), idesc_o, (j | k) != 0);
+                        tc::umma_f16(tmem_O, dP + (uint64_t)(k * 2), dV + (uint64_t)(k * 2), idesc_o, (j | k) != 0);
                     tc::umma_commit(&p_empty[pb]);
                     tc::umma_commit(&kv_empty[s]);
                 }
@@ -276,8 +274,7 @@ extern "C" int regtr_mha_bf16_tc_fwd(const void* QK, int ld_qk, const void* Vt, 
     }
     dim3 grid(regtr_cdiv(max_q_len, BQ), n_heads, n_problems);
     k_mha_bf16_tc<<<grid, 192, SMEM_BYTES, st>>>(tQ, tK, tV, O, ldo, E, q_start, q_len, k_start, k_len,
-                                                 scale * 1.4426950408889634f,
-                                                 getenv("REGTR_MHA_DEBUG") ? atoi(getenv("REGTR_MHA_DEBUG")) : 0);
+                                                 scale * 1.4426950408889634f);
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
 }

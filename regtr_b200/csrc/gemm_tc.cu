@@ -18,8 +18,6 @@
 // B (weights) is split once on the host side of the ABI (regtr_split_tf32) and cached.
 #include <cuda_bf16.h>
 
-#include <cstdlib>
-
 #include "common.cuh"
 #include "tc.cuh"
 
