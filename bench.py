@@ -412,7 +412,12 @@ def main():
         roof = dict(bound='hbm',
                     kernel='k_kpconv_agg (+k_row_flags): KPConv neighbour gather + kernel-point influence + '
                            'aggregation, 11 launches/pair; bytes = SURVEY 8d algorithmic bytes of the KPConv op',
-                    achieved=ach, peak=peak, unit='GB/s', frac=ach / peak, traffic=None, peak_source=peak_src,
+                    achieved=ach, peak=peak, unit='GB/s', frac=ach / peak,
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 11 launches of one
+                    # `ncu --set full` capture of this workload (profiles/r01_ncu_kpconv_agg_summary.csv):
+                    # 58.5 MB per pair against 590 MB algorithmic -- the 126 MB L2 absorbs the row reuse
+                    traffic=58.5e6 / 11, traffic_unit='bytes/launch (ncu capture, batch 1)', peak_source=peak_src,
+                    algorithmic_bytes_per_launch=step_bytes / max(len(last), 1),
                     algorithmic_bytes_per_step=step_bytes, gather_ms_per_step=gather_ms,
                     kpconv_op_ms_per_step_eager=tot_ms, per_launch=per_launch)
 
