@@ -101,11 +101,13 @@ int regtr_kpconv_fwd(const float* q, const float* s, const int32_t* idx, const f
                      float extent, float* out, void* ws, size_t ws_bytes, void* stream);
 
 /* Gather + influence + aggregation stage alone: wf (Nq, 15*Cin), already divided by the
- * neighbour count.  (The HBM-bound "neighbour gather" kernel of the north star.) */
+ * neighbour count.  (The "neighbour gather" kernel of the north star.)  rowflag_ws (Ns bytes):
+ * flags[r] = (sum_c x[r,c] > 0); computed here unless flags_ready != 0 (then it must already hold
+ * them, e.g. from regtr_instnorm_act's rowflag_out). */
 int regtr_kpconv_aggregate(const float* q, const float* s, const int32_t* idx, const float* x,
                            const float* kp, int Nq, int Ns, const int32_t* nq_dev, const int32_t* ns_dev,
                            int K, int Cin, float extent,
-                           float* wf, uint8_t* rowflag_ws, void* stream);
+                           float* wf, uint8_t* rowflag_ws, int flags_ready, void* stream);
 
 /* max over the K gathered rows with a zero shadow row.  Replaces max_pool
  * (kpconv_blocks.py:127-143).  x (Ns,C), idx (Nq,K) i32 -> out (Nq,C). */
@@ -116,11 +118,13 @@ int regtr_max_pool(const float* x, const int32_t* idx, int Nq, int Ns, const int
  * residual add, optional LeakyReLU.  Replaces BatchNormBlock.forward + nn.LeakyReLU
  * (kpconv_blocks.py:497-519, 546-561, 646, 741):  out = act(norm(x) + res).
  * x (n,C); offs (n_clouds+1) i32 device; n_cap >= offs[n_clouds]; res optional (n,C);
- * slope < 0 disables the activation.  In-place (out == x) is allowed. */
+ * slope < 0 disables the activation.  In-place (out == x) is allowed.
+ * rowflag_out (optional, n_cap bytes, C/4 a power of two <= 32): flags[r] = (sum_c out[r,c] > 0),
+ * the neighbour-count predicate of the KPConv that consumes `out`. */
 size_t regtr_instnorm_ws_bytes(int n_cap, int n_clouds, int C);
 int regtr_instnorm_act(const float* x, const int32_t* offs, int n_clouds, int n_cap, int C, float eps,
-                       const float* res, float slope, float* out, void* ws, size_t ws_bytes,
-                       void* stream);
+                       const float* res, float slope, float* out, uint8_t* rowflag_out,
+                       void* ws, size_t ws_bytes, void* stream);
 
 /* ---- dense layers ---------------------------------------------------------------- */
 

@@ -317,14 +317,14 @@ size_t regtr_kpconv_ws_bytes(int Nq, int Ns, int Cin) {
 
 int regtr_kpconv_aggregate(const float* q, const float* s, const int32_t* idx, const float* x, const float* kp,
                            int Nq, int Ns, const int32_t* nq_dev, const int32_t* ns_dev, int K, int Cin, float extent,
-                           float* wf, uint8_t* rowflag_ws, void* stream_) {
+                           float* wf, uint8_t* rowflag_ws, int flags_ready, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (Nq < 0 || Ns < 0 || K <= 0 || K > 128 || Cin <= 0 || !(extent > 0.f)) return REGTR_ERR_ARG;
     if (!(Cin <= 16 || (Cin % 32 == 0 && Cin <= 256 && (Cin / 32 == 1 || Cin / 32 == 2 || Cin / 32 == 4 || Cin / 32 == 8))))
         return REGTR_ERR_UNSUPPORTED;
     if (Nq == 0) return REGTR_OK;
     if (!q || !s || !idx || !x || !kp || !wf || !rowflag_ws) return REGTR_ERR_ARG;
-    if (Ns > 0) {
+    if (Ns > 0 && !flags_ready) {
         k_row_flags<<<regtr_cdiv((long long)Ns * 32, 256), 256, 0, st>>>(x, Ns, Cin, rowflag_ws);
         REGTR_CHECK_LAUNCH();
     }
@@ -355,7 +355,7 @@ int regtr_kpconv_fwd(const float* q, const float* s, const int32_t* idx, const f
     if (ws_bytes < regtr_kpconv_ws_bytes(Nq, Ns, Cin)) return REGTR_ERR_WORKSPACE;
     float* wf = (float*)ws;
     uint8_t* flags = (uint8_t*)ws + regtr_align(sizeof(float) * (size_t)Nq * KP * (size_t)Cin);
-    int rc = regtr_kpconv_aggregate(q, s, idx, x, kp, Nq, Ns, nq_dev, ns_dev, K, Cin, extent, wf, flags, stream_);
+    int rc = regtr_kpconv_aggregate(q, s, idx, x, kp, Nq, Ns, nq_dev, ns_dev, K, Cin, extent, wf, flags, 0, stream_);
     if (rc != REGTR_OK) return rc;
     const int KDs = KP * Cin;
     if (KDs <= 64 && Cout % 4 == 0 && (size_t)KDs * Cout * sizeof(float) <= 48 * 1024) {

@@ -99,28 +99,42 @@ k_in_finalize(const int32_t* __restrict__ offs, int n_clouds, int C, float eps, 
 }
 
 // out = act((x - mean) * rstd + res), float4 per thread; rows beyond offs[n_clouds] are zeroed.
+// FLAGS: additionally emit flags[r] = (sum_c out[r,c] > 0), the "neighbour counts" predicate of the KPConv
+// that consumes `out` (kpconv_blocks.py:409-412), summed in fp64 across the C/4 <= 32 lanes of the row.
+template <bool FLAGS>
 __global__ void k_in_apply(const float* x, const int32_t* __restrict__ offs, int n_clouds, int n_cap, int C,
-                           const float2* __restrict__ stats, const float* res, float slope, float* out) {
+                           const float2* __restrict__ stats, const float* res, float slope, float* out,
+                           uint8_t* __restrict__ flags) {
     const int c4n = C >> 2;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)n_cap * c4n) return;
-    const int r = (int)(t / c4n), c = (int)(t % c4n) * 4;
+    const bool in_range = t < (long long)n_cap * c4n;
+    if (!FLAGS && !in_range) return;
+    const int r = in_range ? (int)(t / c4n) : 0, c = in_range ? (int)(t % c4n) * 4 : 0;
     const size_t o = (size_t)r * C + c;
-    if (r >= offs[n_clouds]) { *reinterpret_cast<float4*>(out + o) = make_float4(0.f, 0.f, 0.f, 0.f); return; }
-    const int cloud = regtr_cloud_of(offs, n_clouds, r);
-    const float4 v = *reinterpret_cast<const float4*>(x + o);
-    const float4 st01 = *reinterpret_cast<const float4*>(stats + (size_t)cloud * C + c);
-    const float4 st23 = *reinterpret_cast<const float4*>(stats + (size_t)cloud * C + c + 2);
-    float y[4] = {(v.x - st01.x) * st01.y, (v.y - st01.z) * st01.w, (v.z - st23.x) * st23.y, (v.w - st23.z) * st23.w};
-    if (res) {
-        const float4 rv = *reinterpret_cast<const float4*>(res + o);
-        y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
-    }
-    if (slope >= 0.f) {
+    const bool live = in_range && r < offs[n_clouds];          // rows beyond the real count are capacity padding
+    float y[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+        const int cloud = regtr_cloud_of(offs, n_clouds, r);
+        const float4 v = *reinterpret_cast<const float4*>(x + o);
+        const float4 st01 = *reinterpret_cast<const float4*>(stats + (size_t)cloud * C + c);
+        const float4 st23 = *reinterpret_cast<const float4*>(stats + (size_t)cloud * C + c + 2);
+        y[0] = (v.x - st01.x) * st01.y; y[1] = (v.y - st01.z) * st01.w;
+        y[2] = (v.z - st23.x) * st23.y; y[3] = (v.w - st23.z) * st23.w;
+        if (res) {
+            const float4 rv = *reinterpret_cast<const float4*>(res + o);
+            y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
+        }
+        if (slope >= 0.f) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) y[j] = y[j] > 0.f ? y[j] : y[j] * slope;
+            for (int j = 0; j < 4; ++j) y[j] = y[j] > 0.f ? y[j] : y[j] * slope;
+        }
     }
-    *reinterpret_cast<float4*>(out + o) = make_float4(y[0], y[1], y[2], y[3]);
+    if (in_range) *reinterpret_cast<float4*>(out + o) = make_float4(y[0], y[1], y[2], y[3]);   // zeros on padding
+    if (FLAGS) {                                               // single convergent shuffle site for the whole warp
+        double acc = ((double)y[0] + (double)y[1]) + ((double)y[2] + (double)y[3]);
+        for (int d = 1; d < c4n; d <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (in_range && (threadIdx.x & (c4n - 1)) == 0) flags[r] = live && acc > 0.0;
+    }
 }
 
 // One warp per row; E <= 1024, multiple of 32.
@@ -177,7 +191,8 @@ size_t regtr_instnorm_ws_bytes(int n_cap, int n_clouds, int C) {
 }
 
 int regtr_instnorm_act(const float* x, const int32_t* offs, int n_clouds, int n_cap, int C, float eps,
-                       const float* res, float slope, float* out, void* ws, size_t ws_bytes, void* stream_) {
+                       const float* res, float slope, float* out, uint8_t* rowflag_out, void* ws, size_t ws_bytes,
+                       void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (!offs || n_clouds <= 0 || n_cap < 0 || C <= 0) return REGTR_ERR_ARG;
     if (C % 4 != 0) return REGTR_ERR_UNSUPPORTED;
@@ -192,8 +207,15 @@ int regtr_instnorm_act(const float* x, const int32_t* offs, int n_clouds, int n_
     REGTR_CHECK_LAUNCH();
     k_in_finalize<<<dim3(n_clouds, regtr_cdiv(C, 32)), block, 0, st>>>(offs, n_clouds, C, eps, partial, stats);
     REGTR_CHECK_LAUNCH();
-    k_in_apply<<<regtr_cdiv((long long)n_cap * (C / 4), 256), 256, 0, st>>>(x, offs, n_clouds, n_cap, C, stats, res,
-                                                                            slope, out);
+    if (rowflag_out) {
+        const int c4n = C / 4;
+        if (c4n > 32 || (c4n & (c4n - 1))) return REGTR_ERR_UNSUPPORTED;   // the row must sit inside one warp
+        k_in_apply<true><<<regtr_cdiv((long long)n_cap * c4n, 256), 256, 0, st>>>(x, offs, n_clouds, n_cap, C, stats,
+                                                                                  res, slope, out, rowflag_out);
+    } else {
+        k_in_apply<false><<<regtr_cdiv((long long)n_cap * (C / 4), 256), 256, 0, st>>>(x, offs, n_clouds, n_cap, C,
+                                                                                      stats, res, slope, out, nullptr);
+    }
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
 }

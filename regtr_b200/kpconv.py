@@ -222,10 +222,11 @@ class KPConv(nn.Module):
         self.kernel_points = nn.Parameter(torch.from_numpy(kernel_disposition(radius, kernel_size)),
                                           requires_grad=False)
 
-    def forward(self, q_pts, s_pts, neighb_inds, x, nq_dev=None, ns_dev=None):
+    def forward(self, q_pts, s_pts, neighb_inds, x, nq_dev=None, ns_dev=None, row_flags=None):
         idx = neighb_inds if neighb_inds.dtype == torch.int32 else neighb_inds.to(torch.int32)
         return ops.kpconv(q_pts.contiguous(), s_pts.contiguous(), idx.contiguous(), x.contiguous(),
-                          self.weights, self.kernel_points, self.KP_extent, nq_dev=nq_dev, ns_dev=ns_dev)
+                          self.weights, self.kernel_points, self.KP_extent, nq_dev=nq_dev, ns_dev=ns_dev,
+                          row_flags=row_flags)
 
     def __repr__(self):
         return 'KPConv(radius: {:.2f}, extent: {:.2f}, in_feat: {:d}, out_feat: {:d})'.format(
@@ -242,9 +243,11 @@ class BatchNormBlock(nn.Module):
         if not use_bn:
             self.bias = nn.Parameter(torch.zeros(in_dim, dtype=torch.float32))
 
-    def fuse(self, x, offs, n_clouds, res=None, slope=-1.0):
+    def fuse(self, x, offs, n_clouds, res=None, slope=-1.0, want_flags=False):
         if self.use_bn:
-            return ops.instnorm_act(x, offs, n_clouds, res=res, slope=slope)
+            return ops.instnorm_act(x, offs, n_clouds, res=res, slope=slope, want_flags=want_flags)
+        if want_flags:
+            raise NotImplementedError('row flags are only fused into the InstanceNorm pass')
         y = x + self.bias
         if res is not None:
             y = y + res
@@ -264,10 +267,10 @@ class UnaryBlock(nn.Module):
         self.mlp = nn.Linear(in_dim, out_dim, bias=False)
         self.batch_norm = BatchNormBlock(out_dim, use_bn, bn_momentum)
 
-    def fuse(self, x, offs, n_clouds, res=None, final_slope=None, m_dev=None):
+    def fuse(self, x, offs, n_clouds, res=None, final_slope=None, m_dev=None, want_flags=False):
         slope = final_slope if final_slope is not None else (-1.0 if self.no_relu else 0.1)
         return self.batch_norm.fuse(ops.linear(x, self.mlp.weight, m_dev=m_dev), offs, n_clouds, res=res,
-                                    slope=slope)
+                                    slope=slope, want_flags=want_flags)
 
     def forward(self, x, stack_lengths=None):
         offs = ops.make_offsets(stack_lengths, x.device)
@@ -315,6 +318,7 @@ class ResnetBottleneckBlock(nn.Module):
         self.block_name, self.layer_ind = block_name, layer_ind
         self.in_dim, self.out_dim = in_dim, out_dim
         bn, mom = config.use_batch_norm, config.batch_norm_momentum
+        self.use_bn = bn
         extent = radius * config.KP_extent / config.conv_radius
         mid = out_dim // 4
         self.unary1 = UnaryBlock(in_dim, mid, bn, mom) if in_dim != mid else nn.Identity()
@@ -329,9 +333,14 @@ class ResnetBottleneckBlock(nn.Module):
 
     def forward(self, features, batch):
         q, s, idx, offs_pre, offs_post, nq_dev, ns_dev, nc = _block_io(self, batch)
-        x = self.unary1.fuse(features, offs_pre, nc, m_dev=ns_dev) if isinstance(self.unary1, UnaryBlock) \
-            else features
-        x = self.KPConv(q, s, idx, x, nq_dev, ns_dev)
+        flags = None
+        if isinstance(self.unary1, UnaryBlock) and self.use_bn:
+            # the normalisation pass also emits the KPConv's "row sums to > 0" neighbour-count flags
+            x, flags = self.unary1.fuse(features, offs_pre, nc, m_dev=ns_dev, want_flags=True)
+        else:
+            x = self.unary1.fuse(features, offs_pre, nc, m_dev=ns_dev) if isinstance(self.unary1, UnaryBlock) \
+                else features
+        x = self.KPConv(q, s, idx, x, nq_dev, ns_dev, row_flags=flags)
         x = self.batch_norm_conv.fuse(x, offs_post, nc, slope=0.1)
         shortcut = ops.max_pool(features, idx, ns_dev) if 'strided' in self.block_name else features
         if isinstance(self.unary_shortcut, UnaryBlock):

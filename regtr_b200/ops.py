@@ -145,7 +145,8 @@ def ball_query(q, q_offs, s, s_offs, grid: CellGrid, K: int, radius: float, q_or
 
 # ------------------------------------------------------------------------ encoder
 
-def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=None, nq_dev=None, ns_dev=None):
+def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=None, nq_dev=None, ns_dev=None,
+           row_flags=None):
     """KPConv.forward (rigid / linear / sum).  idx32 (Nq,K) int32, x (Ns,Cin) -> (Nq,Cout).
     nq_dev / ns_dev: optional 1-element int32 device tensors with the actual counts when the
     leading dimensions are capacities."""
@@ -168,12 +169,12 @@ def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=No
     if GEMM_BACKEND == 'tc3x' and (15 * Cin) % 4 == 0:
         # gather/aggregate kernel, then the [Nq,15Cin] x [15Cin,Cout] contraction on the tensor cores
         wf = ws[:Nq * 15 * Cin * 4].view(torch.float32).view(Nq, 15 * Cin)
-        flags = ws[regtr_align_up(Nq * 15 * Cin * 4):]
+        flags = row_flags if row_flags is not None else ws[regtr_align_up(Nq * 15 * Cin * 4):]
         if 'agg' not in _ABLATE:
           _lib.check(L.regtr_kpconv_aggregate(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(kernel_points), Nq, Ns,
                                             _p(nq_dev), _p(ns_dev), K, Cin, float(extent), _p(wf), _p(flags),
-                                            _stream()), 'regtr_kpconv_aggregate')
-        _count(2)
+                                            1 if row_flags is not None else 0, _stream()), 'regtr_kpconv_aggregate')
+        _count(1 if row_flags is not None else 2)
         hi, lo = split_weight(weights.view(15 * Cin, Cout), transpose=True)
         if ev:
             ev[1].record()
@@ -200,7 +201,7 @@ def kpconv_aggregate(q_pts, s_pts, idx32, x, kernel_points, extent: float, wf=No
     wf = torch.empty((Nq, 15 * Cin), dtype=torch.float32, device=x.device) if wf is None else wf
     flags = workspace(max(Ns, 1), x.device, 'rowflags')
     _lib.check(L.regtr_kpconv_aggregate(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(kernel_points), Nq, Ns,
-                                        _p(nq_dev), _p(ns_dev), K, Cin, float(extent), _p(wf), _p(flags), _stream()),
+                                        _p(nq_dev), _p(ns_dev), K, Cin, float(extent), _p(wf), _p(flags), 0, _stream()),
                'regtr_kpconv_aggregate')
     _count(2)
     return wf
@@ -217,8 +218,10 @@ def max_pool(x, idx32, ns_dev=None):
     return out
 
 
-def instnorm_act(x, offs, n_clouds: int, res=None, slope: float = -1.0, eps: float = 1e-5, out=None):
-    """out = act(InstanceNorm_per_cloud(x) + res); slope < 0 -> no activation."""
+def instnorm_act(x, offs, n_clouds: int, res=None, slope: float = -1.0, eps: float = 1e-5, out=None,
+                 want_flags: bool = False):
+    """out = act(InstanceNorm_per_cloud(x) + res); slope < 0 -> no activation.
+    want_flags: also return the per-row `sum > 0` flags the consuming KPConv needs (uint8, n rows)."""
     L = _lib.load()
     _chk(x, torch.float32, 'x', 2); _chk(offs, torch.int32, 'offs', 1)
     n, C = x.shape
@@ -229,10 +232,13 @@ def instnorm_act(x, offs, n_clouds: int, res=None, slope: float = -1.0, eps: flo
         return out.copy_(x)
     nb = L.regtr_instnorm_ws_bytes(n, n_clouds, C)
     ws = workspace(nb, x.device, 'instnorm')
+    flags = None
+    if want_flags and C // 4 <= 32 and (C // 4) & (C // 4 - 1) == 0 and 'norm' not in _ABLATE:
+        flags = torch.empty(max(n, 1), dtype=torch.uint8, device=x.device)
     _lib.check(L.regtr_instnorm_act(_p(x), _p(offs), n_clouds, n, C, float(eps), _p(res), float(slope), _p(out),
-                                    _p(ws), ws.numel(), _stream()), 'regtr_instnorm_act')
-    _count(2)
-    return out
+                                    _p(flags), _p(ws), ws.numel(), _stream()), 'regtr_instnorm_act')
+    _count(3)
+    return (out, flags) if want_flags else out
 
 
 # -------------------------------------------------------------------- dense layers
