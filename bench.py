@@ -398,7 +398,7 @@ def main():
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                ops.kpconv_aggregate(*info['args'])
+                ops.kpconv_aggregate(*info['args'], row_flags=info.get('row_flags'))
                 e1.record()
                 torch.cuda.synchronize()
                 t = e0.elapsed_time(e1)
@@ -410,7 +410,7 @@ def main():
         peak, peak_src = peaks()
         ach = step_bytes / (gather_ms * 1e-3) / 1e9
         roof = dict(bound='hbm',
-                    kernel='k_kpconv_agg (+k_row_flags): KPConv neighbour gather + kernel-point influence + '
+                    kernel='k_kpconv_agg (+k_row_flags where the flags are not fused upstream): KPConv neighbour gather + kernel-point influence + '
                            'aggregation, 11 launches/pair; bytes = SURVEY 8d algorithmic bytes of the KPConv op',
                     achieved=ach, peak=peak, unit='GB/s', frac=ach / peak,
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 11 launches of one

@@ -189,21 +189,23 @@ def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=No
         ev[2].record()
         trace.append((ev[0], ev[2], dict(Nq=Nq, Ns=Ns, K=K, Cin=Cin, Cout=Cout, idx=idx32,
                                          mid=ev[1] if len(ev) > 3 else None,
-                                         args=(q_pts, s_pts, idx32, x, kernel_points, float(extent)))))
+                                         args=(q_pts, s_pts, idx32, x, kernel_points, float(extent)),
+                                         row_flags=row_flags)))
     return out
 
 
-def kpconv_aggregate(q_pts, s_pts, idx32, x, kernel_points, extent: float, wf=None, nq_dev=None, ns_dev=None):
+def kpconv_aggregate(q_pts, s_pts, idx32, x, kernel_points, extent: float, wf=None, nq_dev=None, ns_dev=None,
+                     row_flags=None):
     """Gather + influence + aggregation only: -> wf (Nq, 15*Cin) (already / neighbour count)."""
     L = _lib.load()
     Nq, K = idx32.shape
     Ns, Cin = x.shape
     wf = torch.empty((Nq, 15 * Cin), dtype=torch.float32, device=x.device) if wf is None else wf
-    flags = workspace(max(Ns, 1), x.device, 'rowflags')
+    flags = row_flags if row_flags is not None else workspace(max(Ns, 1), x.device, 'rowflags')
     _lib.check(L.regtr_kpconv_aggregate(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(kernel_points), Nq, Ns,
-                                        _p(nq_dev), _p(ns_dev), K, Cin, float(extent), _p(wf), _p(flags), 0, _stream()),
-               'regtr_kpconv_aggregate')
-    _count(2)
+                                        _p(nq_dev), _p(ns_dev), K, Cin, float(extent), _p(wf), _p(flags),
+                                        1 if row_flags is not None else 0, _stream()), 'regtr_kpconv_aggregate')
+    _count(1 if row_flags is not None else 2)
     return wf
 
 
