@@ -126,6 +126,42 @@ __global__ void k_gather_sorted(const float* __restrict__ xyz, const unsigned lo
     sxyzi[j] = make_float4(xyz[3 * i + 0], xyz[3 * i + 1], xyz[3 * i + 2], __int_as_float(i));
 }
 
+// Hash table over the occupied cells of a grid: key -> (first sorted position, point count).  Open
+// addressing, linear probing, load factor <= 0.5 (table has >= 2 * n_cap slots).  One lookup replaces
+// a 16-step binary search over the sorted keys.
+struct CellSlot {
+    unsigned long long key;
+    int start;
+    int count;
+};
+static_assert(sizeof(CellSlot) == 16, "CellSlot must be 16 B");
+
+__host__ __device__ inline int cell_table_log2(int n_cap) {
+    int b = 10;
+    while ((1ll << b) < 2ll * (n_cap > 0 ? n_cap : 1)) ++b;
+    return b;
+}
+__device__ __forceinline__ unsigned cell_hash(unsigned long long key, int log2t) {
+    return (unsigned)((key * 0x9E3779B97F4A7C15ull) >> (64 - log2t));
+}
+
+__global__ void k_cell_table_build(const unsigned long long* __restrict__ skeys, int n_cap, CellSlot* __restrict__ table,
+                                   int log2t) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cap) return;
+    const unsigned long long k = skeys[j];
+    if (k == KEY_PAD || (j > 0 && skeys[j - 1] == k)) return;          // not the head of a cell
+    int e = j + 1;
+    while (e < n_cap && skeys[e] == k) ++e;
+    const unsigned mask = (1u << log2t) - 1u;
+    unsigned h = cell_hash(k, log2t);
+    for (;;) {
+        const unsigned long long prev = atomicCAS(&table[h].key, KEY_PAD, k);
+        if (prev == KEY_PAD) { table[h].start = j; table[h].count = e - j; return; }
+        h = (h + 1) & mask;
+    }
+}
+
 // ------------------------------------------------------------------------ ball query
 
 constexpr int BQ_WARPS = 8;
@@ -148,7 +184,7 @@ __device__ __forceinline__ int select_smallest(const int* __restrict__ hits, int
 __global__ void __launch_bounds__(BQ_WARPS * 32)
 k_ball_query(const float* __restrict__ q, const int32_t* __restrict__ q_offs, const int32_t* __restrict__ q_order,
              const int32_t* __restrict__ s_offs, const GridHeader* __restrict__ hdr,
-             const unsigned long long* __restrict__ skeys, const float4* __restrict__ sxyzi, int n_clouds,
+             const CellSlot* __restrict__ table, int log2t, const float4* __restrict__ sxyzi, int n_clouds,
              int nq_cap, int K, float radius, int32_t* __restrict__ out32, long long* __restrict__ out64) {
     __shared__ int s_hits[BQ_WARPS][BQ_HCAP];
     __shared__ int s_sel[BQ_WARPS][BQ_KMAX];
@@ -171,48 +207,66 @@ k_ball_query(const float* __restrict__ q, const int32_t* __restrict__ q_offs, co
     const float cell = hdr->cell;
     const int cx = regtr_cell_of(qx, cell), cy = regtr_cell_of(qy, cell), cz = regtr_cell_of(qz, cell);
     const float r2 = __fmul_rn(radius, radius);
-    const int seg_lo = s_offs[c], seg_hi = s_offs[c + 1];
-
-    // 9 (dx,dy) columns of three z-adjacent cells = 9 contiguous key ranges; lane r searches the lower
-    // bound of range r, lane 9+r its upper bound (18 independent binary searches in parallel)
-    int bound = 0;
-    if (lane < 18) {
-        const int r = lane < 9 ? lane : lane - 9;
-        const int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
-        if (x >= -32767 && x <= 32767 && y >= -32767 && y <= 32767 && cz >= -32767 && cz <= 32766) {
-            const unsigned long long key = lane < 9 ? regtr_pack_key(c, x, y, cz - 1) : regtr_pack_key(c, x, y, cz + 1) + 1ull;
-            bound = lower_bound_u64(skeys, seg_lo, seg_hi, key);
+    // lanes 0..26: one cell of the 3x3x3 stencil each -> hash lookup of (start, count)
+    int c_start = 0, c_cnt = 0;
+    if (lane < 27) {
+        const int x = cx + lane / 9 - 1, y = cy + (lane / 3) % 3 - 1, z = cz + lane % 3 - 1;
+        if (x >= -32767 && x <= 32767 && y >= -32767 && y <= 32767 && z >= -32767 && z <= 32767) {
+            const unsigned long long key = regtr_pack_key(c, x, y, z);
+            const unsigned mask = (1u << log2t) - 1u;
+            unsigned h = cell_hash(key, log2t);
+            for (;;) {
+                const CellSlot sl = table[h];
+                if (sl.key == key) { c_start = sl.start; c_cnt = sl.count; break; }
+                if (sl.key == KEY_PAD) break;
+                h = (h + 1) & mask;
+            }
         }
     }
-    const int lo = bound;
-    const int hi = __shfl_sync(0xffffffffu, bound, (lane + 9) & 31);   // lanes 0..8: their range's upper bound
+    // inclusive prefix sum of the 27 counts: candidate i lives in the first cell whose prefix exceeds i
+    int pre = c_cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, pre, 31);
     int* hits = s_hits[warp];
     int* sel = s_sel[warp];
     int count = 0;
-    for (int r = 0; r < 9; ++r) {
-        const int rlo = __shfl_sync(0xffffffffu, lo, r), rhi = __shfl_sync(0xffffffffu, hi, r);
-        for (int base = rlo; base < rhi; base += 32) {
-            const int j = base + lane;
-            bool hit = false;
-            int sidx = 0;
-            if (j < rhi) {
-                const float4 sp = sxyzi[j];
-                const float dx = __fsub_rn(qx, sp.x), dy = __fsub_rn(qy, sp.y), dz = __fsub_rn(qz, sp.z);
-                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                hit = d2 < r2;
-                sidx = __float_as_int(sp.w);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (count + 32 > BQ_HCAP) {       // staging full: keep only the K smallest so far
-                __syncwarp();
-                const int kept = select_smallest(hits, count, K, sel, lane);
-                for (int t = lane; t < kept; t += 32) hits[t] = sel[t];
-                __syncwarp();
-                count = kept;
-            }
-            if (hit) hits[count + __popc(m & ((1u << lane) - 1u))] = sidx;
-            count += __popc(m);
+    for (int base = 0; base < total; base += 32) {
+        const int i = base + lane;
+        // binary search over the 32 prefix values held one per lane (5 shuffles)
+        int cellid = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int probe = cellid + step - 1;
+            const int pv = __shfl_sync(0xffffffffu, pre, probe);
+            if (pv <= i) cellid += step;
         }
+        const int cell_pre = __shfl_sync(0xffffffffu, pre, cellid);
+        const int cell_cnt = __shfl_sync(0xffffffffu, c_cnt, cellid);
+        const int cell_start = __shfl_sync(0xffffffffu, c_start, cellid);
+        bool hit = false;
+        int sidx = 0;
+        if (i < total) {
+            const int j = cell_start + (i - (cell_pre - cell_cnt));
+            const float4 sp = sxyzi[j];
+            const float dx = __fsub_rn(qx, sp.x), dy = __fsub_rn(qy, sp.y), dz = __fsub_rn(qz, sp.z);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            hit = d2 < r2;
+            sidx = __float_as_int(sp.w);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (count + 32 > BQ_HCAP) {           // staging full: keep only the K smallest so far
+            __syncwarp();
+            const int kept = select_smallest(hits, count, K, sel, lane);
+            for (int t = lane; t < kept; t += 32) hits[t] = sel[t];
+            __syncwarp();
+            count = kept;
+        }
+        if (hit) hits[count + __popc(m & ((1u << lane) - 1u))] = sidx;
+        count += __popc(m);
     }
     __syncwarp();
     const int kept = select_smallest(hits, count, K, sel, lane);
@@ -304,7 +358,8 @@ int regtr_grid_subsample(const float* xyz, const int32_t* offs, int n_clouds, in
 
 size_t regtr_cellgrid_bytes(int n_cap) {
     const size_t n = n_cap > 0 ? (size_t)n_cap : 1;
-    return sizeof(GridHeader) + regtr_align(sizeof(unsigned long long) * n) + regtr_align(sizeof(float4) * n);
+    return sizeof(GridHeader) + regtr_align(sizeof(unsigned long long) * n) + regtr_align(sizeof(float4) * n) +
+           regtr_align(sizeof(CellSlot) << cell_table_log2(n_cap));
 }
 
 size_t regtr_cellgrid_ws_bytes(int n_cap) { return regtr_grid_subsample_ws_bytes(n_cap); }
@@ -332,6 +387,11 @@ int regtr_cellgrid_build(const float* xyz, const int32_t* offs, int n_clouds, in
     REGTR_CHECK_LAUNCH();
     k_gather_sorted<<<regtr_cdiv(n_cap, T), T, 0, st>>>(xyz, skeys, w.vals_out, n_cap, sxyzi, order);
     REGTR_CHECK_LAUNCH();
+    const int log2t = cell_table_log2(n_cap);
+    CellSlot* table = (CellSlot*)((char*)sxyzi + regtr_align(sizeof(float4) * (size_t)n_cap));
+    if (cudaMemsetAsync(table, 0xFF, sizeof(CellSlot) << log2t, st) != cudaSuccess) return REGTR_ERR_ARG;
+    k_cell_table_build<<<regtr_cdiv(n_cap, T), T, 0, st>>>(skeys, n_cap, table, log2t);
+    REGTR_CHECK_LAUNCH();
     return REGTR_OK;
 }
 
@@ -349,8 +409,9 @@ int regtr_ball_query(const float* q, const int32_t* q_offs, const int32_t* q_ord
     const size_t n = s_cap > 0 ? (size_t)s_cap : 1;
     const unsigned long long* skeys = (const unsigned long long*)((const char*)s_grid + sizeof(GridHeader));
     const float4* sxyzi = (const float4*)((const char*)skeys + regtr_align(sizeof(unsigned long long) * n));
+    const CellSlot* table = (const CellSlot*)((const char*)sxyzi + regtr_align(sizeof(float4) * n));
     k_ball_query<<<regtr_cdiv(nq_cap, BQ_WARPS), BQ_WARPS * 32, 0, st>>>(
-        q, q_offs, q_order, s_offs, hdr, skeys, sxyzi, n_clouds, nq_cap, K, radius, out_idx32,
+        q, q_offs, q_order, s_offs, hdr, table, cell_table_log2(s_cap), sxyzi, n_clouds, nq_cap, K, radius, out_idx32,
         (long long*)out_idx64);
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
