@@ -114,21 +114,12 @@ __global__ void k_grid_header(GridHeader* h, float cell, int n_cap) {
     h->n_cap = n_cap;
 }
 
-// sxyzi[j] = (x, y, z, bits(original index)) of the j-th point in cell order.
-__global__ void k_gather_sorted(const float* __restrict__ xyz, const unsigned long long* __restrict__ skeys,
-                                const int32_t* __restrict__ sidx, int n_cap, float4* __restrict__ sxyzi,
-                                int32_t* __restrict__ order) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_cap) return;
-    const int i = sidx[j];
-    if (order) order[j] = i;
-    if (skeys[j] == KEY_PAD) { sxyzi[j] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); return; }
-    sxyzi[j] = make_float4(xyz[3 * i + 0], xyz[3 * i + 1], xyz[3 * i + 2], __int_as_float(i));
-}
+// ---- sort-free cell list: count points per cell in a hash table, prefix-sum the counts, scatter.
+// The order of the points inside a cell (and of the cells in memory) is arbitrary and may differ from
+// run to run; the neighbour search ranks its hits by index afterwards, so its OUTPUT is deterministic.
 
-// Hash table over the occupied cells of a grid: key -> (first sorted position, point count).  Open
-// addressing, linear probing, load factor <= 0.5 (table has >= 2 * n_cap slots).  One lookup replaces
-// a 16-step binary search over the sorted keys.
+// Hash table over the occupied cells of a grid: key -> (first position in the cell-ordered arrays, point
+// count).  Open addressing, linear probing, load factor <= 0.5 (>= 2 * n_cap slots).
 struct CellSlot {
     unsigned long long key;
     int start;
@@ -145,21 +136,53 @@ __device__ __forceinline__ unsigned cell_hash(unsigned long long key, int log2t)
     return (unsigned)((key * 0x9E3779B97F4A7C15ull) >> (64 - log2t));
 }
 
-__global__ void k_cell_table_build(const unsigned long long* __restrict__ skeys, int n_cap, CellSlot* __restrict__ table,
-                                   int log2t) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_cap) return;
-    const unsigned long long k = skeys[j];
-    if (k == KEY_PAD || (j > 0 && skeys[j - 1] == k)) return;          // not the head of a cell
-    int e = j + 1;
-    while (e < n_cap && skeys[e] == k) ++e;
+// slot_of[i] = table slot of point i's cell (inserted on first sight); cnt[slot] += 1.
+__global__ void k_cell_count(const float* __restrict__ xyz, const int32_t* __restrict__ offs, int n_clouds, int n_cap,
+                             float cell, unsigned long long* __restrict__ tkeys, int32_t* __restrict__ cnt, int log2t,
+                             int32_t* __restrict__ slot_of, uint32_t* status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cap) return;
+    if (i >= offs[n_clouds]) { slot_of[i] = -1; return; }
+    const int c = regtr_cloud_of(offs, n_clouds, i);
+    const int vx = clamp_coord(regtr_cell_of(xyz[3 * i + 0], cell), status);
+    const int vy = clamp_coord(regtr_cell_of(xyz[3 * i + 1], cell), status);
+    const int vz = clamp_coord(regtr_cell_of(xyz[3 * i + 2], cell), status);
+    const unsigned long long key = regtr_pack_key(c, vx, vy, vz);
     const unsigned mask = (1u << log2t) - 1u;
-    unsigned h = cell_hash(k, log2t);
+    unsigned h = cell_hash(key, log2t);
     for (;;) {
-        const unsigned long long prev = atomicCAS(&table[h].key, KEY_PAD, k);
-        if (prev == KEY_PAD) { table[h].start = j; table[h].count = e - j; return; }
+        const unsigned long long prev = atomicCAS(&tkeys[h], KEY_PAD, key);
+        if (prev == KEY_PAD || prev == key) break;
         h = (h + 1) & mask;
     }
+    atomicAdd(&cnt[h], 1);
+    slot_of[i] = (int)h;
+}
+
+// position of point i = start[slot] + (arrival rank inside the cell); pads keep the tail positions.
+__global__ void k_cell_scatter(const float* __restrict__ xyz, const int32_t* __restrict__ offs, int n_clouds, int n_cap,
+                               const int32_t* __restrict__ slot_of, const int32_t* __restrict__ start,
+                               int32_t* __restrict__ cursor, float4* __restrict__ sxyzi, int32_t* __restrict__ order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cap) return;
+    const int h = slot_of[i];
+    if (h < 0) {                                   // capacity padding: identity tail of the permutation
+        sxyzi[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        if (order) order[i] = i;
+        return;
+    }
+    const int pos = start[h] + atomicAdd(&cursor[h], 1);
+    sxyzi[pos] = make_float4(xyz[3 * i + 0], xyz[3 * i + 1], xyz[3 * i + 2], __int_as_float(i));
+    if (order) order[pos] = i;
+}
+
+__global__ void k_cell_pack(const unsigned long long* __restrict__ tkeys, const int32_t* __restrict__ start,
+                            const int32_t* __restrict__ cnt, int t_size, CellSlot* __restrict__ table) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= t_size) return;
+    CellSlot s;
+    s.key = tkeys[h]; s.start = start[h]; s.count = cnt[h];
+    table[h] = s;
 }
 
 // ------------------------------------------------------------------------ ball query
@@ -356,13 +379,46 @@ int regtr_grid_subsample(const float* xyz, const int32_t* offs, int n_clouds, in
     return REGTR_OK;
 }
 
-size_t regtr_cellgrid_bytes(int n_cap) {
-    const size_t n = n_cap > 0 ? (size_t)n_cap : 1;
-    return sizeof(GridHeader) + regtr_align(sizeof(unsigned long long) * n) + regtr_align(sizeof(float4) * n) +
-           regtr_align(sizeof(CellSlot) << cell_table_log2(n_cap));
+// grid buffer: [GridHeader | sxyzi (n float4) | CellSlot table (2^log2t)]
+static inline float4* grid_sxyzi(void* grid) { return (float4*)((char*)grid + sizeof(GridHeader)); }
+static inline CellSlot* grid_table(void* grid, size_t n) {
+    return (CellSlot*)((char*)grid + sizeof(GridHeader) + regtr_align(sizeof(float4) * n));
 }
 
-size_t regtr_cellgrid_ws_bytes(int n_cap) { return regtr_grid_subsample_ws_bytes(n_cap); }
+size_t regtr_cellgrid_bytes(int n_cap) {
+    const size_t n = n_cap > 0 ? (size_t)n_cap : 1;
+    return sizeof(GridHeader) + regtr_align(sizeof(float4) * n) + regtr_align(sizeof(CellSlot) << cell_table_log2(n_cap));
+}
+
+// workspace: slot_of (n) | zero-initialised block [tkeys (T u64) | cnt (T) | cursor (T)] | start (T + 1) | cub scan temp
+struct GridWs {
+    int32_t* slot_of;
+    unsigned long long* tkeys;
+    int32_t *cnt, *cursor, *start;
+    void* cub_tmp;
+    size_t cub_bytes, zero_bytes, total;
+};
+
+static GridWs carve_grid(void* ws, int n_cap) {
+    GridWs w;
+    char* p = (char*)ws;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += regtr_align(bytes); return (void*)r; };
+    const size_t t = (size_t)1 << cell_table_log2(n_cap);
+    w.slot_of = (int32_t*)take(sizeof(int32_t) * (size_t)(n_cap > 0 ? n_cap : 1));
+    w.tkeys = (unsigned long long*)take(sizeof(unsigned long long) * t);
+    w.cnt = (int32_t*)take(sizeof(int32_t) * t);
+    w.cursor = (int32_t*)take(sizeof(int32_t) * t);
+    w.zero_bytes = (size_t)((char*)w.cursor - (char*)w.cnt) + regtr_align(sizeof(int32_t) * t);   // cnt + cursor
+    w.start = (int32_t*)take(sizeof(int32_t) * t);
+    w.cub_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, w.cub_bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int)t, (cudaStream_t)0);
+    w.cub_tmp = take(w.cub_bytes);
+    w.total = off;
+    return w;
+}
+
+size_t regtr_cellgrid_ws_bytes(int n_cap) { return carve_grid(nullptr, n_cap).total; }
 
 int regtr_cellgrid_build(const float* xyz, const int32_t* offs, int n_clouds, int n_cap, float cell, void* grid,
                          int32_t* order, uint32_t* status, void* ws, size_t ws_bytes, void* stream_) {
@@ -374,23 +430,26 @@ int regtr_cellgrid_build(const float* xyz, const int32_t* offs, int n_clouds, in
     REGTR_CHECK_LAUNCH();
     if (n_cap == 0) return REGTR_OK;
     if (!xyz || !ws) return REGTR_ERR_ARG;
-    SubWs w = carve(ws, n_cap);
+    GridWs w = carve_grid(ws, n_cap);
     if (ws_bytes < w.total) return REGTR_ERR_WORKSPACE;
-    unsigned long long* skeys = (unsigned long long*)((char*)grid + sizeof(GridHeader));
-    float4* sxyzi = (float4*)((char*)skeys + regtr_align(sizeof(unsigned long long) * (size_t)n_cap));
+    const int log2t = cell_table_log2(n_cap);
+    const int t_size = 1 << log2t;
+    float4* sxyzi = grid_sxyzi(grid);
+    CellSlot* table = grid_table(grid, (size_t)n_cap);
     const int T = 256;
-    k_make_keys<<<regtr_cdiv(n_cap, T), T, 0, st>>>(xyz, offs, n_clouds, n_cap, cell, w.keys_in, w.vals_in, status);
+    if (cudaMemsetAsync(w.tkeys, 0xFF, sizeof(unsigned long long) * (size_t)t_size, st) != cudaSuccess ||
+        cudaMemsetAsync(w.cnt, 0, w.zero_bytes, st) != cudaSuccess)
+        return REGTR_ERR_ARG;
+    k_cell_count<<<regtr_cdiv(n_cap, T), T, 0, st>>>(xyz, offs, n_clouds, n_cap, cell, w.tkeys, w.cnt, log2t, w.slot_of,
+                                                     status);
     REGTR_CHECK_LAUNCH();
     size_t tb = w.cub_bytes;
-    cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys_in, skeys, w.vals_in, w.vals_out, n_cap, 0,
-                                    key_bits(n_clouds), st);
+    cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.cnt, w.start, t_size, st);
     REGTR_CHECK_LAUNCH();
-    k_gather_sorted<<<regtr_cdiv(n_cap, T), T, 0, st>>>(xyz, skeys, w.vals_out, n_cap, sxyzi, order);
+    k_cell_scatter<<<regtr_cdiv(n_cap, T), T, 0, st>>>(xyz, offs, n_clouds, n_cap, w.slot_of, w.start, w.cursor, sxyzi,
+                                                       order);
     REGTR_CHECK_LAUNCH();
-    const int log2t = cell_table_log2(n_cap);
-    CellSlot* table = (CellSlot*)((char*)sxyzi + regtr_align(sizeof(float4) * (size_t)n_cap));
-    if (cudaMemsetAsync(table, 0xFF, sizeof(CellSlot) << log2t, st) != cudaSuccess) return REGTR_ERR_ARG;
-    k_cell_table_build<<<regtr_cdiv(n_cap, T), T, 0, st>>>(skeys, n_cap, table, log2t);
+    k_cell_pack<<<regtr_cdiv(t_size, T), T, 0, st>>>(w.tkeys, w.start, w.cnt, t_size, table);
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
 }
@@ -407,9 +466,8 @@ int regtr_ball_query(const float* q, const int32_t* q_offs, const int32_t* q_ord
     if (!q || (!out_idx32 && !out_idx64)) return REGTR_ERR_ARG;
     const GridHeader* hdr = (const GridHeader*)s_grid;
     const size_t n = s_cap > 0 ? (size_t)s_cap : 1;
-    const unsigned long long* skeys = (const unsigned long long*)((const char*)s_grid + sizeof(GridHeader));
-    const float4* sxyzi = (const float4*)((const char*)skeys + regtr_align(sizeof(unsigned long long) * n));
-    const CellSlot* table = (const CellSlot*)((const char*)sxyzi + regtr_align(sizeof(float4) * n));
+    const float4* sxyzi = grid_sxyzi(const_cast<void*>(s_grid));
+    const CellSlot* table = grid_table(const_cast<void*>(s_grid), n);
     k_ball_query<<<regtr_cdiv(nq_cap, BQ_WARPS), BQ_WARPS * 32, 0, st>>>(
         q, q_offs, q_order, s_offs, hdr, table, cell_table_log2(s_cap), sxyzi, n_clouds, nq_cap, K, radius, out_idx32,
         (long long*)out_idx64);

@@ -121,7 +121,7 @@ class CellGrid:
         _lib.check(L.regtr_cellgrid_build(_p(xyz), _p(offs), n_clouds, self.n_cap, self.cell, _p(self.buf),
                                           _p(self.order), _p(status), _p(ws), ws.numel(), _stream()),
                    'regtr_cellgrid_build')
-        _count(3)
+        _count(4)
 
 
 def ball_query(q, q_offs, s, s_offs, grid: CellGrid, K: int, radius: float, q_order=None,
