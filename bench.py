@@ -244,6 +244,8 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'   # keep stdout to the single JSON line (NCCL prints its banner there)
         dist.init_process_group('nccl', device_id=dev)
     W = max(args.warmup, 3)
     K = args.steps
