@@ -376,3 +376,27 @@ def test_pipelined_executor_matches_serial():
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+def test_graphed_executor_batch_of_two_pairs():
+    """B=2 through the CUDA-graph executor: per-pair poses equal the eager forward's, lists have
+    the reference's layout (B entries per key)."""
+    from regtr_b200.config import get_config
+    from regtr_b200.regtr import GraphedRegTR, RegTR
+    from regtr_b200.synthetic import make_3dmatch_pair
+    from regtr_b200.weights import random_state_dict
+    cfg = get_config('3dmatch')
+    model = RegTR(cfg).to(DEV).eval()
+    model.load_state_dict(random_state_dict(cfg, 10), strict=True)
+    ps = [make_3dmatch_pair(2500 + i, 4000 + 1500 * i) for i in range(2)]
+    mk = lambda: {'src_xyz': [G(p['src_xyz']) for p in ps], 'tgt_xyz': [G(p['tgt_xyz']) for p in ps]}
+    want, b_e = model(mk()), None
+    runner = GraphedRegTR(model, bucket=16384)
+    b_g = mk()
+    got = runner(b_g)
+    assert got['pose'].shape == (6, 2, 3, 4) and len(got['src_feat']) == 2 and len(got['tgt_kp_warped']) == 2
+    assert float((got['pose'] - want['pose']).abs().max()) <= 5e-5
+    for b in range(2):
+        assert got['src_kp'][b].shape == want['src_kp'][b].shape and torch.equal(got['src_kp'][b], want['src_kp'][b])
+        assert got['src_overlap'][b].shape == want['src_overlap'][b].shape
+    assert [int(v) for v in b_g['kpconv_meta']['stack_lengths'][0]] == [len(p['src_xyz']) for p in ps] + [len(p['tgt_xyz']) for p in ps]
