@@ -206,19 +206,25 @@ def run_reference(args, rank, world):
     log(f'reference arm: {cores} threads of {os.cpu_count()} cores')
     for i in range(max(args.warmup, 1)):
         run(*pool[i % len(pool)])
-    # each step = a bounded sample of the workload: ONE pair (the workload has B*N pairs/step)
+    # each step = a bounded sample of the workload: ONE pair (the workload has B*N pairs/step); the run is
+    # additionally bounded in time (REGTR_REF_BUDGET_S, default 120 s) so that large K still ends in minutes
+    budget = float(os.environ.get('REGTR_REF_BUDGET_S', 120))
     t0 = time.perf_counter()
+    done = 0
     for i in range(args.steps):
         run(*pool[i % len(pool)])
+        done += 1
+        if done >= 3 and time.perf_counter() - t0 > budget:
+            break
     dt = time.perf_counter() - t0
-    v = args.steps / dt
+    v = done / dt
     line = dict(metric='pairs/sec on 3DMatch-size clouds (~20k pts); pose err vs ref', value=v, unit='pairs/s',
-                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1000 * dt / args.steps,
+                n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1000 * dt / done,
                 higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                impl='reference',
+                impl='reference', executed_steps=done,
                 config=dict(workload=workload_name(args, B), sample='1 pair per step (bounded sample)'),
                 cpu_baseline=dict(value=v, unit='pairs/s', cores=cores, kind='port',
-                                  sample=f'{args.steps} steps x 1 pair; pre-processing = {pre_kind}'),
+                                  sample=f'{done} steps x 1 pair; pre-processing = {pre_kind}'),
                 e2e=dict(value=v, unit='pairs/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line), flush=True)
