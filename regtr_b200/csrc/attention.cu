@@ -70,8 +70,8 @@ k_mha_fp32(const float* __restrict__ Q, int ldq, const float* __restrict__ Kp, i
                 sdot = fmaf(qv[4 * d + 2], t.z, sdot); sdot = fmaf(qv[4 * d + 3], t.w, sdot);
             }
             const float mn = fmaxf(m, sdot);
-            const float corr = expf(m - mn);             // exp(-inf) = 0 on the first key
-            const float p = expf(sdot - mn);
+            const float corr = exp2f(m - mn);            // scores carry log2(e): exp2(-inf) = 0 on the first key
+            const float p = exp2f(sdot - mn);
             l = l * corr + p;
             const float4* vr = reinterpret_cast<const float4*>(&sV[j][0]);
 #pragma unroll
@@ -91,7 +91,7 @@ k_mha_fp32(const float* __restrict__ Q, int ldq, const float* __restrict__ Kp, i
     float mg = -INFINITY;
 #pragma unroll
     for (int t = 0; t < KSPLIT; ++t) mg = fmaxf(mg, sM[t][lane]);
-    const float w = (m == -INFINITY) ? 0.f : expf(m - mg);
+    const float w = (m == -INFINITY) ? 0.f : exp2f(m - mg);
     sL[ks][lane] = l * w;
     // reuse sK as the accumulator exchange buffer: [KSPLIT][QT][HD] floats = 16 KB = sizeof(sK)
     float* xb = &sK[0][0];
@@ -150,8 +150,9 @@ extern "C" int regtr_mha_varlen_fwd(const float* Q, int ldq, const float* K, int
     if (!Q || !K || !V || !O || !q_start || !q_len || !k_start || !k_len) return REGTR_ERR_ARG;
     if ((ldq | ldk | ldv) % 4 != 0 || n_problems > 65535 || n_heads > 65535) return REGTR_ERR_ARG;
     dim3 grid(regtr_cdiv(max_q_len, QT), n_heads, n_problems);
+    // softmax in base 2: q is pre-scaled by scale * log2(e) (<= 2 ulp exp2f instead of two ~20-instruction expf)
     k_mha_fp32<<<grid, QT * KSPLIT, 0, st>>>(Q, ldq, K, ldk, V, ldv, O, ldo, q_start, q_len, k_start, k_len, n_heads,
-                                            scale);
+                                            scale * 1.4426950408889634f);
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
 }
