@@ -7,6 +7,7 @@
 //   models/backbone_kpconv/kpconv_blocks.py:127-143  max_pool
 #include <cublas_v2.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -179,7 +180,245 @@ k_kpconv_agg(const float* __restrict__ q, const float* __restrict__ s, const int
     }
 }
 
-// Small Cin (1..16, e.g. the constant-1 input feature of the first block): same staging; then lane
+// ---- aggregation on the tensor cores ---------------------------------------------------------------
+// Per query the aggregation is a tiny GEMM  wf[15, Cin] = H[15, n] @ X[n, Cin]  (H = influences of the
+// n <= K valid neighbours, X = their gathered feature rows).  One warp per query runs it as
+// mma.sync m16n8k8 (M = 16 kernel-point rows, k-step = 8 neighbours) with both operands built
+// directly in the fragment layout -- no shared-memory staging of H and one 128-byte row read per
+// neighbour (LDG.128: lane (g,t) reads channels 4g..4g+3 of neighbours t and t+4):
+//   A (H^T, 16x8):  lane (g,t) computes the influences of kernel points g, g+8 on neighbours t, t+4
+//   B (X, 8x8):     n-tile j takes column n=g from channel 32h + 4g + j  (a fixed channel permutation)
+//   D (16x8):       lane (g,t) ends up with 8 contiguous channels 32h + 8t .. 8t+7 of rows g and g+8
+// fp32 accuracy comes from the 3xTF32 split (lo*hi + hi*lo + hi*hi, round-to-nearest hi), like the GEMMs.
+// round-to-nearest (ties away) TF32 head of a finite fp32 value: two integer ops instead of cvt.rna's
+// special-case sequence; the tail x - head is exact in fp32 and the tensor core truncates it to TF32.
+__device__ __forceinline__ uint32_t tf32_head(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// linear influence max(0, 1 - |rel - kp| / extent); sqrt.approx: one MUFU, exact 0 at 0, <= 1 ulp
+__device__ __forceinline__ float influence(const float4 r, float kx, float ky, float kz, float inv_extent) {
+    const float dx = r.x - kx, dy = r.y - ky, dz = r.z - kz;
+    const float d2 = dx * dx + dy * dy + dz * dz;
+    float d;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(d2));
+    return fmaxf(0.f, fmaf(-d, inv_extent, 1.f));
+}
+
+// NH = 32-channel groups per warp; blockIdx.y selects the warp's channel slice [32 NH y, 32 NH (y+1)) so
+// that small levels with wide features still fill the machine (each slice repeats the cheap staging).
+template <int NH, int MINB>
+__global__ void __launch_bounds__(AGG_WARPS * 32, MINB)
+k_kpconv_agg_mma(const float* __restrict__ q, const float* __restrict__ s, const int32_t* __restrict__ idx,
+                 const float* __restrict__ x, const uint8_t* __restrict__ flags, const float* __restrict__ kp,
+                 int Nq, int Ns, const int32_t* __restrict__ nq_dev, const int32_t* __restrict__ ns_dev, int K, int Cin,
+                 float inv_extent, float* __restrict__ wf) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Kp = (K + 7) & ~7;
+    // per warp: rows[Kp][32 NH] (staged feature rows, 16-byte chunks swizzled) | rel[Kp] (float4) | id[Kp]
+    constexpr int ROW = 32 * NH;                  // floats per staged row
+    float* rows_s = reinterpret_cast<float*>(smem_raw) + (size_t)warp * Kp * (ROW + 5);
+    float4* rel_s = reinterpret_cast<float4*>(rows_s + Kp * ROW);
+    int* id_s = reinterpret_cast<int*>(rows_s + Kp * (ROW + 4));
+    const int qi = blockIdx.x * AGG_WARPS + warp;
+    if (qi >= Nq) return;
+    if (ns_dev) Ns = min(Ns, *ns_dev);
+    const int c_base = blockIdx.y * (32 * NH);
+    const int g = lane >> 2, t = lane & 3;
+    float* out = wf + (size_t)qi * (KP * Cin) + c_base;
+    if (nq_dev && qi >= *nq_dev) {               // capacity padding row: zeros
+        for (int p = g; p < KP; p += 8)
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                reinterpret_cast<float4*>(out + p * Cin + 32 * h + 8 * t)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                reinterpret_cast<float4*>(out + p * Cin + 32 * h + 8 * t)[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        return;
+    }
+    // compact the valid (non-shadow) neighbours; count those whose feature row sums to > 0
+    const float qx = q[3 * qi], qy = q[3 * qi + 1], qz = q[3 * qi + 2];
+    const int32_t* idx_row = idx + (size_t)qi * K;
+    int base = 0, counted = 0;
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int kk = k0 + lane;
+        int id = Ns;
+        if (kk < K) id = idx_row[kk];
+        const bool valid = (id >= 0) && (id < Ns);
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            rel_s[pos] = make_float4(s[3 * id + 0] - qx, s[3 * id + 1] - qy, s[3 * id + 2] - qz, 0.f);
+            id_s[pos] = id;
+            counted += flags[id];
+        }
+        base += __popc(m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, o);
+    // pad to a whole k-step with a loadable row id and a far-away position (influence exactly 0)
+    const int padded = (base + 7) & ~7;
+    if (lane < padded - base) { id_s[base + lane] = base > 0 ? id_s[0] : 0; rel_s[base + lane] = make_float4(1e6f, 1e6f, 1e6f, 0.f); }
+    __syncwarp();
+
+    // stage ALL neighbour rows of the query with cp.async (16 bytes per lane): every row is in flight at
+    // once instead of one k-step at a time.  Chunk c of row n lands in slot (c + 2 (n & 3)) & 7 of its
+    // 128-byte group so that the LDS.128 fragment reads below are bank-conflict free.
+    {
+        constexpr int CPR = 8 * NH, RPI = 32 / CPR;            // 16-byte chunks per row, rows per warp instruction
+        const int c = lane % CPR, rg = lane / CPR;
+        const float* xs = x + c_base + 4 * c;
+        uint32_t dst = (uint32_t)__cvta_generic_to_shared(rows_s) + (uint32_t)(rg * ROW + (c & ~7) * 4) * 4u;
+        for (int n = rg; n < padded; n += RPI, dst += RPI * ROW * 4) {
+            const float* src = xs + (size_t)id_s[n] * Cin;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(((c + 2 * n) & 7) * 16)), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
+    const float ax = __ldg(kp + 3 * g), ay = __ldg(kp + 3 * g + 1), az = __ldg(kp + 3 * g + 2);
+    const bool row_b = g + 8 < KP;                // M = 16 rows, kernel points 0..14; row 15: far away -> 0
+    const float bx = row_b ? __ldg(kp + 3 * g + 24) : -1e6f, by = row_b ? __ldg(kp + 3 * g + 25) : -1e6f,
+                bz = row_b ? __ldg(kp + 3 * g + 26) : -1e6f;
+
+    float acc[NH][4][4];
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[h][j][e] = 0.f;
+
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    for (int k0 = 0; k0 < padded; k0 += 8) {
+        const int n0 = k0 + t, n1 = n0 + 4;        // n0 & 3 == n1 & 3 == t
+        const float* row0 = rows_s + n0 * ROW + 4 * ((g + 2 * t) & 7);
+        const float* row1 = rows_s + n1 * ROW + 4 * ((g + 2 * t) & 7);
+        float4 v0[NH], v1[NH];
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            v0[h] = *reinterpret_cast<const float4*>(row0 + 32 * h);
+            v1[h] = *reinterpret_cast<const float4*>(row1 + 32 * h);
+        }
+        const float4 r0 = rel_s[n0], r1 = rel_s[n1];
+        const float w[4] = {influence(r0, ax, ay, az, inv_extent), influence(r0, bx, by, bz, inv_extent),
+                            influence(r1, ax, ay, az, inv_extent), influence(r1, bx, by, bz, inv_extent)};
+        uint32_t a_hi[4], a_lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { a_hi[e] = tf32_head(w[e]); a_lo[e] = __float_as_uint(w[e] - __uint_as_float(a_hi[e])); }
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            const float b0f[4] = {v0[h].x, v0[h].y, v0[h].z, v0[h].w};
+            const float b1f[4] = {v1[h].x, v1[h].y, v1[h].z, v1[h].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t h0 = tf32_head(b0f[j]), h1 = tf32_head(b1f[j]);
+                const uint32_t l0 = __float_as_uint(b0f[j] - __uint_as_float(h0));
+                const uint32_t l1 = __float_as_uint(b1f[j] - __uint_as_float(h1));
+                mma_tf32_16x8x8(acc[h][j], a_lo, h0, h1);
+                mma_tf32_16x8x8(acc[h][j], a_hi, l0, l1);
+                mma_tf32_16x8x8(acc[h][j], a_hi, h0, h1);
+            }
+        }
+    }
+
+    float inv;                                    // 1 / max(count, 1): one MUFU (<= 1 ulp)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"((float)max(counted, 1)));
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+        float* o = out + g * Cin + 32 * h + 8 * t;
+        reinterpret_cast<float4*>(o)[0] = make_float4(acc[h][0][0] * inv, acc[h][1][0] * inv, acc[h][2][0] * inv, acc[h][3][0] * inv);
+        reinterpret_cast<float4*>(o)[1] = make_float4(acc[h][0][1] * inv, acc[h][1][1] * inv, acc[h][2][1] * inv, acc[h][3][1] * inv);
+        if (row_b) {
+            float* o2 = o + 8 * Cin;
+            reinterpret_cast<float4*>(o2)[0] = make_float4(acc[h][0][2] * inv, acc[h][1][2] * inv, acc[h][2][2] * inv, acc[h][3][2] * inv);
+            reinterpret_cast<float4*>(o2)[1] = make_float4(acc[h][0][3] * inv, acc[h][1][3] * inv, acc[h][2][3] * inv, acc[h][3][3] * inv);
+        }
+    }
+}
+
+// Cin = 1 (the first block: a constant-1 input feature).  Per query the whole op is
+//   wf[p] = sum_k h(rel_k - kp_p) * x[id_k] / #{k : x[id_k] > 0}       (15 numbers)
+// and, FUSEd, out[c] = sum_p wf[p] W[p, c].  Lane (p = lane & 15, half = lane >> 4) sums its kernel point over
+// every second neighbour straight from the staged (rel, x) quadruples: no influence table, no gather in the loop.
+template <bool FUSE>
+__global__ void __launch_bounds__(AGG_WARPS * 32)
+k_kpconv_c1(const float* __restrict__ q, const float* __restrict__ s, const int32_t* __restrict__ idx,
+            const float* __restrict__ x, const float* __restrict__ kp, const float* __restrict__ W, int Nq, int Ns,
+            const int32_t* __restrict__ nq_dev, const int32_t* __restrict__ ns_dev, int K, int Cout, float inv_extent,
+            float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4* rel_s = reinterpret_cast<float4*>(smem_raw) + warp * K;
+    float* W_s = reinterpret_cast<float*>(reinterpret_cast<float4*>(smem_raw) + AGG_WARPS * K);
+    if (FUSE) {
+        for (int t = threadIdx.x; t < KP * Cout; t += blockDim.x) W_s[t] = W[t];
+        __syncthreads();
+    }
+    const int qi = blockIdx.x * AGG_WARPS + warp;
+    if (qi >= Nq) return;
+    if (ns_dev) Ns = min(Ns, *ns_dev);
+    const int width = FUSE ? Cout : KP;
+    float* o = out + (size_t)qi * width;
+    if (nq_dev && qi >= *nq_dev) {               // capacity padding row: zeros
+        for (int t = lane; t < width; t += 32) o[t] = 0.f;
+        return;
+    }
+    const float qx = q[3 * qi], qy = q[3 * qi + 1], qz = q[3 * qi + 2];
+    const int32_t* idx_row = idx + (size_t)qi * K;
+    int base = 0, counted = 0;
+#pragma unroll 1
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int kk = k0 + lane;
+        int id = Ns;
+        if (kk < K) id = idx_row[kk];
+        const bool valid = (id >= 0) && (id < Ns);
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const float xv = x[id];
+            rel_s[base + __popc(m & ((1u << lane) - 1u))] =
+                make_float4(s[3 * id + 0] - qx, s[3 * id + 1] - qy, s[3 * id + 2] - qz, xv);
+            counted += xv > 0.f;                 // the reference counts rows whose feature sum is > 0
+        }
+        base += __popc(m);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, off);
+    __syncwarp();
+    const int p = lane & 15;
+    const bool real = p < KP;                    // slot 15: a far-away kernel point, influence exactly 0
+    const float kx = real ? __ldg(kp + 3 * p) : -1e6f, ky = real ? __ldg(kp + 3 * p + 1) : -1e6f,
+                kz = real ? __ldg(kp + 3 * p + 2) : -1e6f;
+    float acc = 0.f;
+    for (int k = lane >> 4; k < base; k += 2) {
+        const float4 r = rel_s[k];
+        acc = fmaf(influence(r, kx, ky, kz, inv_extent), r.w, acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"((float)max(counted, 1)));
+    const float v = acc * inv;
+    if constexpr (!FUSE) {
+        if (lane < KP) o[lane] = v;
+    } else {
+        for (int c0 = 0; c0 < Cout; c0 += 32) {  // warp-uniform trip count: the shuffles stay convergent
+            const int c = c0 + lane;
+            float r = 0.f;
+#pragma unroll
+            for (int pp = 0; pp < KP; ++pp) {
+                const float wv = __shfl_sync(0xffffffffu, v, pp);
+                if (c < Cout) r = fmaf(wv, W_s[pp * Cout + c], r);
+            }
+            if (c < Cout) o[c] = r;
+        }
+    }
+}
+
+// Small Cin (2..16): same staging; then lane
 // (p, half) sums w[k][p] * x[id_k][c] over its half of the neighbours, halves combined by shuffle.
 __global__ void __launch_bounds__(AGG_WARPS * 32)
 k_kpconv_agg_small(const float* __restrict__ q, const float* __restrict__ s, const int32_t* __restrict__ idx,
@@ -306,6 +545,38 @@ int launch_agg(const float* q, const float* s, const int32_t* idx, const float* 
     return REGTR_OK;
 }
 
+template <int NH, int MINB>
+int launch_agg_mma(const float* q, const float* s, const int32_t* idx, const float* x, const uint8_t* flags,
+                   const float* kp, int Nq, int Ns, const int32_t* nq_dev, const int32_t* ns_dev, int K, int Cin,
+                   float extent, float* wf, cudaStream_t st) {
+    const int Kp = (K + 7) & ~7;
+    const size_t smem = (size_t)AGG_WARPS * Kp * (32 * NH + 5) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_kpconv_agg_mma<NH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return REGTR_ERR_UNSUPPORTED;       // K too large for the staged kernel
+    }
+    const dim3 grid(regtr_cdiv(Nq, AGG_WARPS), Cin / (32 * NH));
+    k_kpconv_agg_mma<NH, MINB><<<grid, AGG_WARPS * 32, smem, st>>>(q, s, idx, x, flags, kp, Nq, Ns, nq_dev, ns_dev, K, Cin,
+                                                                   1.f / extent, wf);
+    REGTR_CHECK_LAUNCH();
+    return REGTR_OK;
+}
+
+// channel groups per warp: as wide as possible while the grid still has >= min_warps warps
+int agg_mma_nh(int Nq, int Cin) {
+    const char* e = getenv("REGTR_AGG_MIN_WARPS");          // tuning knob, default from the level-size sweep
+    const int min_warps = e ? atoi(e) : 8192;
+    int nh = Cin / 32 > 2 ? 2 : Cin / 32;      // staged rows: 128 NH bytes of smem per neighbour and warp
+    while (nh > 1 && (long long)Nq * (Cin / (32 * nh)) < min_warps) nh >>= 1;
+    return nh;
+}
+
+// REGTR_AGG_IMPL=ffma selects the CUDA-core aggregation kernels (A/B measurements); default: tensor cores.
+bool agg_use_mma() {
+    const char* e = getenv("REGTR_AGG_IMPL");
+    return !(e && e[0] == 'f');
+}
+
 }  // namespace
 
 extern "C" {
@@ -324,6 +595,12 @@ int regtr_kpconv_aggregate(const float* q, const float* s, const int32_t* idx, c
         return REGTR_ERR_UNSUPPORTED;
     if (Nq == 0) return REGTR_OK;
     if (!q || !s || !idx || !x || !kp || !wf || !rowflag_ws) return REGTR_ERR_ARG;
+    if (Cin == 1 && (size_t)AGG_WARPS * K * sizeof(float4) <= 48 * 1024) {      // flags come from x itself
+        k_kpconv_c1<false><<<regtr_cdiv(Nq, AGG_WARPS), AGG_WARPS * 32, (size_t)AGG_WARPS * K * sizeof(float4), st>>>(
+            q, s, idx, x, kp, nullptr, Nq, Ns, nq_dev, ns_dev, K, 0, 1.f / extent, wf);
+        REGTR_CHECK_LAUNCH();
+        return REGTR_OK;
+    }
     if (Ns > 0 && !flags_ready) {
         k_row_flags<<<regtr_cdiv((long long)Ns * 32, 256), 256, 0, st>>>(x, Ns, Cin, rowflag_ws);
         REGTR_CHECK_LAUNCH();
@@ -335,6 +612,14 @@ int regtr_kpconv_aggregate(const float* q, const float* s, const int32_t* idx, c
                                                                                    Ns, nq_dev, ns_dev, K, Cin, extent, wf);
         REGTR_CHECK_LAUNCH();
         return REGTR_OK;
+    }
+    if (agg_use_mma()) {
+        int rc = REGTR_ERR_UNSUPPORTED;
+        switch (agg_mma_nh(Nq, Cin)) {
+            case 1: rc = launch_agg_mma<1, 4>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, Cin, extent, wf, st); break;
+            case 2: rc = launch_agg_mma<2, 2>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, Cin, extent, wf, st); break;
+        }
+        if (rc != REGTR_ERR_UNSUPPORTED) return rc;
     }
     switch (Cin / 32) {
         case 1: return launch_agg<1, 4, 5>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, extent, wf, st);
@@ -353,6 +638,17 @@ int regtr_kpconv_fwd(const float* q, const float* s, const int32_t* idx, const f
     if (Nq == 0) return REGTR_OK;
     if (!W || !out || !ws) return REGTR_ERR_ARG;
     if (ws_bytes < regtr_kpconv_ws_bytes(Nq, Ns, Cin)) return REGTR_ERR_WORKSPACE;
+    if (Cin == 1) {                               // first block: gather + aggregation + 15 x Cout contraction, one kernel
+        if (K <= 0 || K > 128 || !(extent > 0.f)) return REGTR_ERR_ARG;
+        if (!q || !s || !idx || !x || !kp) return REGTR_ERR_ARG;
+        const size_t smem = (size_t)AGG_WARPS * K * sizeof(float4) + (size_t)KP * Cout * sizeof(float);
+        if (smem <= 48 * 1024) {
+            k_kpconv_c1<true><<<regtr_cdiv(Nq, AGG_WARPS), AGG_WARPS * 32, smem, st>>>(
+                q, s, idx, x, kp, W, Nq, Ns, nq_dev, ns_dev, K, Cout, 1.f / extent, out);
+            REGTR_CHECK_LAUNCH();
+            return REGTR_OK;
+        }
+    }
     float* wf = (float*)ws;
     uint8_t* flags = (uint8_t*)ws + regtr_align(sizeof(float) * (size_t)Nq * KP * (size_t)Cin);
     int rc = regtr_kpconv_aggregate(q, s, idx, x, kp, Nq, Ns, nq_dev, ns_dev, K, Cin, extent, wf, flags, 0, stream_);

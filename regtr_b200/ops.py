@@ -184,7 +184,7 @@ def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=No
         _lib.check(L.regtr_kpconv_fwd(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(weights), _p(kernel_points), Nq, Ns,
                                       _p(nq_dev), _p(ns_dev), K, Cin, Cout, float(extent), _p(out), _p(ws),
                                       ws.numel(), _stream()), 'regtr_kpconv_fwd')
-        _count(2)
+        _count(1 if Cin == 1 else 3)
     if ev:
         ev[2].record()
         trace.append((ev[0], ev[2], dict(Nq=Nq, Ns=Ns, K=K, Cin=Cin, Cout=Cout, idx=idx32,
@@ -205,7 +205,7 @@ def kpconv_aggregate(q_pts, s_pts, idx32, x, kernel_points, extent: float, wf=No
     _lib.check(L.regtr_kpconv_aggregate(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(kernel_points), Nq, Ns,
                                         _p(nq_dev), _p(ns_dev), K, Cin, float(extent), _p(wf), _p(flags),
                                         1 if row_flags is not None else 0, _stream()), 'regtr_kpconv_aggregate')
-    _count(1 if row_flags is not None else 2)
+    _count(1 if (row_flags is not None or Cin == 1) else 2)
     return wf
 
 
