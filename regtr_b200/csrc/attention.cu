@@ -1,4 +1,5 @@
-// Variable-length multi-head attention core, fp32 CUDA-core parity path.
+// Variable-length multi-head attention core, fp32-accurate parity path: a tensor-core kernel
+// (mma.sync 3xTF32, the default) and the CUDA-core kernel it replaced (REGTR_MHA_IMPL=ffma).
 //
 // Replaces the softmax(QK^T/sqrt(d))V core of nn.MultiheadAttention as called by
 // TransformerCrossEncoderLayer.forward_pre (/root/reference/src/models/transformer/
@@ -6,10 +7,12 @@
 // padded keys with -inf; here every (query range, key range) problem is explicit, which is
 // equivalent because masked keys receive exactly zero weight.
 //
-// Work decomposition: block = (problem, head, tile of 32 queries); 4 warps split the keys
+// CUDA-core kernel, work decomposition: block = (problem, head, tile of 32 queries); 4 warps split the keys
 // 4 ways (key j handled by warp j % 4), each thread keeps one query row (32 floats), an
 // online-softmax state and a 32-float accumulator; K/V tiles of 128 keys are staged in
 // shared memory and read as warp-wide broadcasts; the 4 partial states are merged at the end.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -116,6 +119,165 @@ k_mha_fp32(const float* __restrict__ Q, int ldq, const float* __restrict__ Kp, i
     }
 }
 
+// ---- tensor-core fp32-accurate core (default) ------------------------------------------------------
+// Flash-attention on mma.sync m16n8k8 TF32 with the 3xTF32 split (x = hi + lo; hi*hi + hi*lo + lo*hi in
+// fp32 accumulators), so scores and outputs keep fp32 accuracy while the 2 x 32 MACs per (query, key)
+// run on the tensor cores.  Block = (problem, head, 64 queries): 4 warps x 16 query rows; keys stream
+// through shared memory in chunks of 64, already split into hi/lo halves once per block.
+//   S = Q K^T:  A = Q fragment (registers, pre-scaled by scale*log2e, split once), B = K[key g][d]
+//   online softmax on the C fragments (rows g, g+8; quad shuffles for the row maxima; row sums stay
+//   lane-local until the end)
+//   O += P V:   the C fragment of S is reused as the A fragment of P under the key permutation
+//               (A column t <-> key 2t, column t+4 <-> key 2t+1); B = V[key][d] with the same permutation.
+// Row stride 36 floats makes every fragment LDS bank-conflict free.
+constexpr int MQ = 64, MK = 64, MLD = 36;
+
+__device__ __forceinline__ uint32_t tf32_head(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float fast_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__global__ void __launch_bounds__(128)
+k_mha_tf32x3(const float* __restrict__ Q, int ldq, const float* __restrict__ Kp, int ldk, const float* __restrict__ Vp,
+             int ldv, float* __restrict__ O, int ldo, const int32_t* __restrict__ q_start,
+             const int32_t* __restrict__ q_len, const int32_t* __restrict__ k_start, const int32_t* __restrict__ k_len,
+             float scale) {
+    __shared__ __align__(16) float sKh[MK][MLD], sKl[MK][MLD], sVh[MK][MLD], sVl[MK][MLD];
+    const int prob = blockIdx.z, head = blockIdx.y, tile = blockIdx.x;
+    const int ql = q_len[prob];
+    if (tile * MQ >= ql) return;
+    const int q0 = q_start[prob], k0 = k_start[prob], kl = k_len[prob];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int col = head * HD;
+    const int r0 = tile * MQ + warp * 16 + g, r1 = r0 + 8;      // this lane's two query rows (within the problem)
+
+    // Q fragments: a0 (r0, 8kk+t)  a1 (r1, 8kk+t)  a2 (r0, 8kk+t+4)  a3 (r1, 8kk+t+4)
+    uint32_t qh[4][4], qlo[4][4];
+    {
+        const float* p0 = Q + (size_t)(q0 + min(r0, ql - 1)) * ldq + col;
+        const float* p1 = Q + (size_t)(q0 + min(r1, ql - 1)) * ldq + col;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const float v[4] = {p0[8 * kk + t] * scale, p1[8 * kk + t] * scale, p0[8 * kk + t + 4] * scale,
+                                p1[8 * kk + t + 4] * scale};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { qh[kk][e] = tf32_head(v[e]); qlo[kk][e] = __float_as_uint(v[e] - __uint_as_float(qh[kk][e])); }
+        }
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    for (int kb = 0; kb < kl; kb += MK) {
+        __syncthreads();
+        // stage + split one chunk of keys / values (zeros beyond the key range)
+#pragma unroll
+        for (int j = 0; j < (MK * 8) / 128; ++j) {
+            const int f = threadIdx.x + 128 * j, r = f >> 3, c4 = f & 7;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (kb + r < kl) {
+                kv = __ldg(reinterpret_cast<const float4*>(Kp + (size_t)(k0 + kb + r) * ldk + col) + c4);
+                vv = __ldg(reinterpret_cast<const float4*>(Vp + (size_t)(k0 + kb + r) * ldv + col) + c4);
+            }
+            const float kx[4] = {kv.x, kv.y, kv.z, kv.w}, vx[4] = {vv.x, vv.y, vv.z, vv.w};
+            float kh[4], kl4[4], vh[4], vl4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                kh[e] = __uint_as_float(tf32_head(kx[e])); kl4[e] = kx[e] - kh[e];
+                vh[e] = __uint_as_float(tf32_head(vx[e])); vl4[e] = vx[e] - vh[e];
+            }
+            *reinterpret_cast<float4*>(&sKh[r][4 * c4]) = make_float4(kh[0], kh[1], kh[2], kh[3]);
+            *reinterpret_cast<float4*>(&sKl[r][4 * c4]) = make_float4(kl4[0], kl4[1], kl4[2], kl4[3]);
+            *reinterpret_cast<float4*>(&sVh[r][4 * c4]) = make_float4(vh[0], vh[1], vh[2], vh[3]);
+            *reinterpret_cast<float4*>(&sVl[r][4 * c4]) = make_float4(vl4[0], vl4[1], vl4[2], vl4[3]);
+        }
+        __syncthreads();
+
+        // S = Q K^T over the chunk: 8 n-tiles of 8 keys
+        float S[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) S[nt][e] = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t bh0 = __float_as_uint(sKh[8 * nt + g][8 * kk + t]), bh1 = __float_as_uint(sKh[8 * nt + g][8 * kk + t + 4]);
+                const uint32_t bl0 = __float_as_uint(sKl[8 * nt + g][8 * kk + t]), bl1 = __float_as_uint(sKl[8 * nt + g][8 * kk + t + 4]);
+                mma_tf32(S[nt], qlo[kk], bh0, bh1);
+                mma_tf32(S[nt], qh[kk], bl0, bl1);
+                mma_tf32(S[nt], qh[kk], bh0, bh1);
+            }
+        }
+        if (kb + MK > kl) {                      // last chunk: keys beyond the range get zero weight
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const int key = kb + 8 * nt + 2 * t;
+                if (key >= kl) { S[nt][0] = -INFINITY; S[nt][2] = -INFINITY; }
+                if (key + 1 >= kl) { S[nt][1] = -INFINITY; S[nt][3] = -INFINITY; }
+            }
+        }
+        // online softmax (base 2: the scores carry log2 e)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            mx0 = fmaxf(mx0, fmaxf(S[nt][0], S[nt][1]));
+            mx1 = fmaxf(mx1, fmaxf(S[nt][2], S[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);       // finite: every chunk holds >= 1 valid key
+        const float c0 = fast_exp2(m0 - mn0), c1 = fast_exp2(m1 - mn1);   // exp2(-inf) = 0 on the first chunk
+        m0 = mn0; m1 = mn1;
+        l0 *= c0; l1 *= c1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[j][0] *= c0; acc[j][1] *= c0; acc[j][2] *= c1; acc[j][3] *= c1; }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            S[nt][0] = fast_exp2(S[nt][0] - mn0); S[nt][1] = fast_exp2(S[nt][1] - mn0);
+            S[nt][2] = fast_exp2(S[nt][2] - mn1); S[nt][3] = fast_exp2(S[nt][3] - mn1);
+            l0 += S[nt][0] + S[nt][1];
+            l1 += S[nt][2] + S[nt][3];
+        }
+        // O += P V
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            // A fragment of P: a0 (r0, key 2t) a1 (r1, key 2t) a2 (r0, key 2t+1) a3 (r1, key 2t+1)
+            const float pv[4] = {S[nt][0], S[nt][2], S[nt][1], S[nt][3]};
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { ph[e] = tf32_head(pv[e]); pl[e] = __float_as_uint(pv[e] - __uint_as_float(ph[e])); }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t bh0 = __float_as_uint(sVh[8 * nt + 2 * t][8 * j + g]), bh1 = __float_as_uint(sVh[8 * nt + 2 * t + 1][8 * j + g]);
+                const uint32_t bl0 = __float_as_uint(sVl[8 * nt + 2 * t][8 * j + g]), bl1 = __float_as_uint(sVl[8 * nt + 2 * t + 1][8 * j + g]);
+                mma_tf32(acc[j], pl, bh0, bh1);
+                mma_tf32(acc[j], ph, bl0, bl1);
+                mma_tf32(acc[j], ph, bh0, bh1);
+            }
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    // C fragment: (r0, 8j+2t), (r0, 8j+2t+1), (r1, 8j+2t), (r1, 8j+2t+1)
+    if (r0 < ql) {
+        float* dst = O + (size_t)(q0 + r0) * ldo + col + 2 * t;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float2*>(dst + 8 * j) = make_float2(acc[j][0] * i0, acc[j][1] * i0);
+    }
+    if (r1 < ql) {
+        float* dst = O + (size_t)(q0 + r1) * ldo + col + 2 * t;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float2*>(dst + 8 * j) = make_float2(acc[j][2] * i1, acc[j][3] * i1);
+    }
+}
+
 // plan[0..4)[c]: q_start, q_len, cross k_start, cross k_len for cloud c of a (src x B, tgt x B) stack.
 __global__ void k_attention_plan(const int32_t* __restrict__ offs, int B, int32_t* __restrict__ plan) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -149,6 +311,14 @@ extern "C" int regtr_mha_varlen_fwd(const float* Q, int ldq, const float* K, int
     if (n_problems == 0 || max_q_len == 0) return REGTR_OK;
     if (!Q || !K || !V || !O || !q_start || !q_len || !k_start || !k_len) return REGTR_ERR_ARG;
     if ((ldq | ldk | ldv) % 4 != 0 || n_problems > 65535 || n_heads > 65535) return REGTR_ERR_ARG;
+    const char* impl = getenv("REGTR_MHA_IMPL");           // "ffma": CUDA-core kernel (A/B measurements)
+    if (!(impl && impl[0] == 'f') && (ldo % 2) == 0) {
+        dim3 grid(regtr_cdiv(max_q_len, MQ), n_heads, n_problems);
+        k_mha_tf32x3<<<grid, 128, 0, st>>>(Q, ldq, K, ldk, V, ldv, O, ldo, q_start, q_len, k_start, k_len,
+                                          scale * 1.4426950408889634f);
+        REGTR_CHECK_LAUNCH();
+        return REGTR_OK;
+    }
     dim3 grid(regtr_cdiv(max_q_len, QT), n_heads, n_problems);
     // softmax in base 2: q is pre-scaled by scale * log2(e) (<= 2 ulp exp2f instead of two ~20-instruction expf)
     k_mha_fp32<<<grid, QT * KSPLIT, 0, st>>>(Q, ldq, K, ldk, V, ldv, O, ldo, q_start, q_len, k_start, k_len, n_heads,
