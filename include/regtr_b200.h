@@ -177,6 +177,18 @@ int regtr_mha_varlen_fwd(const float* Q, int ldq, const float* K, int ldk, const
                          const int32_t* k_start, const int32_t* k_len, int n_problems,
                          int max_q_len, int n_heads, int head_dim, float scale, void* stream);
 
+/* CorrespondenceDecoder.simple_attention (regtr.py:316-351, the `direct_regress_coor: False` branch):
+ * single-head attention whose values are the key coordinates,
+ *   out[l, q] = sum_k softmax_k(Qp[l, q] . Kp[l, k] * scale) xyz[k]          (fp32)
+ * for all n_layers decoder inputs at once.  Qp/Kp: (n_layers * n_rows, D) row-major with leading
+ * dimension ld -- the q_proj / k_proj outputs; row l*n_rows + t belongs to token t of layer l.
+ * xyz (n_rows, 3): token coordinates; out (n_layers * n_rows, 3).  Problem tables as for
+ * regtr_mha_varlen_fwd (token ranges, shared by all layers).  D % 4 == 0. */
+int regtr_corr_decode_fwd(const float* Qp, const float* Kp, int ld, const float* xyz, float* out,
+                          const int32_t* q_start, const int32_t* q_len, const int32_t* k_start,
+                          const int32_t* k_len, int n_problems, int max_q_len, int n_layers, int n_rows,
+                          int D, float scale, void* stream);
+
 /* Tensor-core attention core (bf16 operands, fp32 TMEM accumulation, fp32 softmax): the "fast"
  * precision mode of the same nn.MultiheadAttention core (transformers.py:197-226), head_dim 32.
  * Inputs are produced by regtr_gemm_tf32x3_qkv_bf16 (the packed in-projection with a bf16

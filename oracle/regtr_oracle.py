@@ -123,6 +123,16 @@ def pos_embed_sine(xyz, d_model=256, temperature=10000.0, scale=1.0):
     return F.pad(emb, (0, d_model - npf * n_dim))
 
 
+def pos_embed_learned(sd, xyz, prefix='pos_embed.'):
+    """PositionEmbeddingLearned.forward (transformer/position_embedding.py:53-72): 5-layer MLP, ReLU between."""
+    h = xyz
+    for i in (0, 2, 4, 6, 8):
+        h = h @ sd[f'{prefix}mlp.{i}.weight'].to(xyz.dtype).t() + sd[f'{prefix}mlp.{i}.bias'].to(xyz.dtype)
+        if i != 8:
+            h = F.relu(h)
+    return h
+
+
 def mha(q_in, k_in, v_in, in_w, in_b, out_w, out_b, nhead):
     """nn.MultiheadAttention forward on ONE un-padded sequence pair (no mask needed):
     packed in-projection, per-head softmax(q k^T / sqrt(dh)) v, out-projection.
@@ -142,7 +152,6 @@ def cross_encoder(sd, cfg, src, tgt, src_pe, tgt_pe, prefix='transformer_encoder
     """TransformerCrossEncoder.forward with return_intermediate and final norm
     (transformers.py:27-59) over TransformerCrossEncoderLayer.forward_pre (183-244).
     Operates per pair on un-padded sequences; returns (L,S,E), (L,T,E)."""
-    assert cfg.pre_norm, 'forward_post is outside the hot path (SURVEY.md 2 row 4)'
     E, H = cfg.d_embed, cfg.nhead
     dt = src.dtype
     g = lambda k: sd[prefix + k].to(dt)
@@ -155,6 +164,20 @@ def cross_encoder(sd, cfg, src, tgt, src_pe, tgt_pe, prefix='transformer_encoder
         p = f'layers.{i}.'
         att = lambda m, q, k, v: mha(q, k, v, g(p + m + '.in_proj_weight'), g(p + m + '.in_proj_bias'),
                                      g(p + m + '.out_proj.weight'), g(p + m + '.out_proj.bias'), H)
+        ffn = lambda x: F.relu(x @ g(p + 'linear1.weight').t() + g(p + 'linear1.bias')) \
+            @ g(p + 'linear2.weight').t() + g(p + 'linear2.bias')
+        if not cfg.pre_norm:                              # forward_post (transformers.py:121-181)
+            swp, twp = src + sp, tgt + tp
+            src = ln(src + att('self_attn', swp, swp, swp if cfg.sa_val_has_pos_emb else src), p + 'norm1')
+            tgt = ln(tgt + att('self_attn', twp, twp, twp if cfg.sa_val_has_pos_emb else tgt), p + 'norm1')
+            swp, twp = src + sp, tgt + tp
+            s3 = att('multihead_attn', swp, twp, twp if cfg.ca_val_has_pos_emb else tgt)
+            t3 = att('multihead_attn', twp, swp, swp if cfg.ca_val_has_pos_emb else src)
+            src, tgt = ln(src + s3, p + 'norm2'), ln(tgt + t3, p + 'norm2')
+            src, tgt = ln(src + ffn(src), p + 'norm3'), ln(tgt + ffn(tgt), p + 'norm3')
+            outs_s.append(src)                            # no final norm without pre_norm (regtr.py:64)
+            outs_t.append(tgt)
+            continue
         s2 = ln(src, p + 'norm1'); s2p = s2 + sp
         src = src + att('self_attn', s2p, s2p, s2p if cfg.sa_val_has_pos_emb else s2)
         t2 = ln(tgt, p + 'norm1'); t2p = t2 + tp
@@ -164,8 +187,6 @@ def cross_encoder(sd, cfg, src, tgt, src_pe, tgt_pe, prefix='transformer_encoder
         s3 = att('multihead_attn', s2p, t2p, t2p if cfg.ca_val_has_pos_emb else t2)
         t3 = att('multihead_attn', t2p, s2p, s2p if cfg.ca_val_has_pos_emb else s2)
         src, tgt = src + s3, tgt + t3
-        ffn = lambda x: F.relu(x @ g(p + 'linear1.weight').t() + g(p + 'linear1.bias')) \
-            @ g(p + 'linear2.weight').t() + g(p + 'linear2.bias')
         src = src + ffn(ln(src, p + 'norm3'))
         tgt = tgt + ffn(ln(tgt, p + 'norm3'))
         outs_s.append(ln(src, 'norm'))
@@ -180,6 +201,23 @@ def regressor(sd, feats, prefix='correspondence_decoder.'):
     h = F.relu(h @ g('coor_mlp.2.weight').t() + g('coor_mlp.2.bias'))
     corr = h @ g('coor_mlp.4.weight').t() + g('coor_mlp.4.bias')
     logit = feats @ g('conf_logits_decoder.weight').t() + g('conf_logits_decoder.bias')
+    return corr, logit
+
+
+def corr_decoder(sd, cfg, feats_q, feats_k, pe_q, pe_k, xyz_k, prefix='correspondence_decoder.'):
+    """CorrespondenceDecoder (regtr.py:297-396) for one direction of one pair, un-padded:
+    feats_q (L,Q,E), feats_k (L,S,E) conditioned features, pe_* position embeddings, xyz_k (S,3).
+    simple_attention (316-351): q = q_proj(f_q + pe)/sqrt(E), k = k_proj(f_k + pe), softmax over keys,
+    weighted sum of the key coordinates; logits from the plain features (383).  q_norm is unused (306)."""
+    g = lambda k: sd[prefix + k].to(feats_q.dtype)
+    use_pe = cfg.corr_decoder_has_pos_emb
+    fq = feats_q + pe_q if use_pe else feats_q
+    fk = feats_k + pe_k if use_pe else feats_k
+    q = (fq @ g('q_proj.weight').t() + g('q_proj.bias')) / math.sqrt(fq.shape[-1])
+    k = fk @ g('k_proj.weight').t() + g('k_proj.bias')
+    attn = torch.softmax(q @ k.transpose(-2, -1), dim=-1)               # (L,Q,S)
+    corr = attn @ xyz_k
+    logit = feats_q @ g('conf_logits_decoder.weight').t() + g('conf_logits_decoder.bias')
     return corr, logit
 
 
@@ -208,7 +246,6 @@ def forward(sd, cfg, src_list, tgt_list, dtype=torch.float32, meta=None, with_up
     float stages); by default the oracle pre-processing in oracle/pre.py is used.
     Returns the reference's output dict (torch CPU tensors) plus 'kpconv_meta'.
     """
-    assert cfg.get('direct_regress_coor', False), 'CorrespondenceDecoder is a "next" row (SURVEY 8f N4)'
     B = len(src_list)
     if meta is None:
         meta = pre.preprocess(cfg, list(src_list) + list(tgt_list), with_upsamples)
@@ -216,7 +253,10 @@ def forward(sd, cfg, src_list, tgt_list, dtype=torch.float32, meta=None, with_up
     feats = encoder(sd, cfg, meta, dtype)
     both = feats @ sd['feat_proj.weight'].to(dtype).t() + sd['feat_proj.bias'].to(dtype)
     xyz_c = _t(meta['points'][-1], dtype)
-    pe = pos_embed_sine(xyz_c, cfg.d_embed, scale=cfg.get('pos_emb_scaling', 1.0))
+    if cfg.get('pos_emb_type', 'sine') == 'sine':
+        pe = pos_embed_sine(xyz_c, cfg.d_embed, scale=cfg.get('pos_emb_scaling', 1.0))
+    else:
+        pe = pos_embed_learned({k: v.to(dtype) for k, v in sd.items() if k.startswith('pos_embed.')}, xyz_c)
     f_split, x_split, p_split = (torch.split(v, slens) for v in (both, xyz_c, pe))
     out = {k: [] for k in ('src_feat_un', 'tgt_feat_un', 'src_feat', 'tgt_feat', 'src_kp', 'tgt_kp',
                            'src_kp_warped', 'tgt_kp_warped', 'src_overlap', 'tgt_overlap')}
@@ -225,8 +265,12 @@ def forward(sd, cfg, src_list, tgt_list, dtype=torch.float32, meta=None, with_up
         fs, ft = f_split[b], f_split[B + b]
         xs, xt = x_split[b], x_split[B + b]
         cs, ct = cross_encoder(sd, cfg, fs, ft, p_split[b], p_split[B + b])
-        s_corr, s_log = regressor(sd, cs)
-        t_corr, t_log = regressor(sd, ct)
+        if cfg.get('direct_regress_coor', False):
+            s_corr, s_log = regressor(sd, cs)
+            t_corr, t_log = regressor(sd, ct)
+        else:
+            s_corr, s_log = corr_decoder(sd, cfg, cs, ct, p_split[b], p_split[B + b], xt)
+            t_corr, t_log = corr_decoder(sd, cfg, ct, cs, p_split[B + b], p_split[b], xs)
         L = cs.shape[0]
         a = torch.cat([xs.expand(L, -1, -1), t_corr], 1)               # regtr.py:185-190
         bb = torch.cat([s_corr, xt.expand(L, -1, -1)], 1)

@@ -74,12 +74,17 @@ def regtr_modelnet() -> Cfg:
     return Cfg(c)
 
 
-def get_config(name: str) -> Cfg:
+def get_config(name: str, **overrides) -> Cfg:
+    """Named config; keyword overrides select the alternative branches (e.g. `pre_norm=False`,
+    `direct_regress_coor=False`, `pos_emb_type='learned'`)."""
     if name in ('3dmatch', 'regtr_3dmatch'):
-        return regtr_3dmatch()
-    if name in ('modelnet', 'regtr_modelnet'):
-        return regtr_modelnet()
-    raise KeyError(f'unknown config {name!r}')
+        cfg = regtr_3dmatch()
+    elif name in ('modelnet', 'regtr_modelnet'):
+        cfg = regtr_modelnet()
+    else:
+        raise KeyError(f'unknown config {name!r}')
+    cfg.update(overrides)
+    return cfg
 
 
 def load_config(path: str) -> Cfg:

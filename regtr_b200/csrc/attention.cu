@@ -278,6 +278,95 @@ k_mha_tf32x3(const float* __restrict__ Q, int ldq, const float* __restrict__ Kp,
     }
 }
 
+// ---- CorrespondenceDecoder.simple_attention (regtr.py:316-351) ---------------------------------------
+// Single-head attention whose values are key COORDINATES: out[q] = sum_k softmax_k(Qp[q] . Kp[k] * scale) xyz[k],
+// for every decoder layer l at once (rows l*n_rows + token of Qp/Kp).  Block = (16 queries, problem, layer):
+// warp w owns queries 4w..4w+3, lane = key of the current 32-key chunk; keys and queries are staged
+// TRANSPOSED ([d][key], [d][query]) so that the D-long dot products read conflict-free / broadcast.
+constexpr int CQ = 16, CK = 32;
+
+__global__ void __launch_bounds__(128)
+k_corr_attention(const float* __restrict__ Qp, const float* __restrict__ Kp, int ld, const float* __restrict__ xyz,
+                 float* __restrict__ out, const int32_t* __restrict__ q_start, const int32_t* __restrict__ q_len,
+                 const int32_t* __restrict__ k_start, const int32_t* __restrict__ k_len, int n_rows, int D,
+                 float scale) {
+    extern __shared__ __align__(16) float smem_f[];
+    float* sQt = smem_f;                       // [D][CQ]
+    float* sKt = sQt + (size_t)D * CQ;          // [D][CK]
+    float* sX = sKt + (size_t)D * CK;           // [CK][4]
+    const int tile = blockIdx.x, prob = blockIdx.y, layer = blockIdx.z;
+    const int ql = q_len[prob];
+    if (tile * CQ >= ql) return;
+    const int q0 = q_start[prob], k0 = k_start[prob], kl = k_len[prob];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t row_base = (size_t)layer * n_rows;
+    const int d4 = D >> 2;
+    for (int f = threadIdx.x; f < CQ * d4; f += 128) {          // queries, pre-scaled (softmax in base 2)
+        const int r = f % CQ, c = f / CQ;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tile * CQ + r < ql) v = __ldg(reinterpret_cast<const float4*>(Qp + (row_base + q0 + tile * CQ + r) * ld) + c);
+        sQt[(4 * c + 0) * CQ + r] = v.x * scale; sQt[(4 * c + 1) * CQ + r] = v.y * scale;
+        sQt[(4 * c + 2) * CQ + r] = v.z * scale; sQt[(4 * c + 3) * CQ + r] = v.w * scale;
+    }
+    float m[4], l[4], a[4][3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { m[i] = -INFINITY; l[i] = 0.f; a[i][0] = a[i][1] = a[i][2] = 0.f; }
+
+    for (int kb = 0; kb < kl; kb += CK) {
+        __syncthreads();
+        for (int f = threadIdx.x; f < CK * d4; f += 128) {
+            const int r = f % CK, c = f / CK;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kb + r < kl) v = __ldg(reinterpret_cast<const float4*>(Kp + (row_base + k0 + kb + r) * ld) + c);
+            sKt[(4 * c + 0) * CK + r] = v.x; sKt[(4 * c + 1) * CK + r] = v.y;
+            sKt[(4 * c + 2) * CK + r] = v.z; sKt[(4 * c + 3) * CK + r] = v.w;
+        }
+        if (threadIdx.x < CK) {
+            const bool ok = kb + threadIdx.x < kl;
+            const float* xr = xyz + (size_t)(k0 + kb + threadIdx.x) * 3;
+            sX[4 * threadIdx.x + 0] = ok ? xr[0] : 0.f;
+            sX[4 * threadIdx.x + 1] = ok ? xr[1] : 0.f;
+            sX[4 * threadIdx.x + 2] = ok ? xr[2] : 0.f;
+        }
+        __syncthreads();
+        float sc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+        for (int d = 0; d < D; ++d) {
+            const float kv = sKt[d * CK + lane];
+            const float4 q4 = *reinterpret_cast<const float4*>(sQt + d * CQ + 4 * warp);
+            sc[0] = fmaf(kv, q4.x, sc[0]); sc[1] = fmaf(kv, q4.y, sc[1]);
+            sc[2] = fmaf(kv, q4.z, sc[2]); sc[3] = fmaf(kv, q4.w, sc[3]);
+        }
+        const bool live = kb + lane < kl;
+        const float vx = sX[4 * lane], vy = sX[4 * lane + 1], vz = sX[4 * lane + 2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float sv = live ? sc[i] : -INFINITY;
+            float mx = sv;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const float mn = fmaxf(m[i], mx);                   // finite: the chunk holds >= 1 live key
+            const float corr = exp2f(m[i] - mn), p = live ? exp2f(sv - mn) : 0.f;
+            l[i] = l[i] * corr + p;
+            a[i][0] = fmaf(p, vx, a[i][0] * corr); a[i][1] = fmaf(p, vy, a[i][1] * corr); a[i][2] = fmaf(p, vz, a[i][2] * corr);
+            m[i] = mn;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float r[4] = {l[i], a[i][0], a[i][1], a[i][2]};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r[e] += __shfl_xor_sync(0xffffffffu, r[e], o);
+        const int qi = tile * CQ + 4 * warp + i;
+        if (lane < 3 && qi < ql) {
+            const float inv = r[0] > 0.f ? 1.f / r[0] : 0.f;
+            out[(row_base + q0 + qi) * 3 + lane] = (lane == 0 ? r[1] : lane == 1 ? r[2] : r[3]) * inv;
+        }
+    }
+}
+
 // plan[0..4)[c]: q_start, q_len, cross k_start, cross k_len for cloud c of a (src x B, tgt x B) stack.
 __global__ void k_attention_plan(const int32_t* __restrict__ offs, int B, int32_t* __restrict__ plan) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,6 +412,29 @@ extern "C" int regtr_mha_varlen_fwd(const float* Q, int ldq, const float* K, int
     // softmax in base 2: q is pre-scaled by scale * log2(e) (<= 2 ulp exp2f instead of two ~20-instruction expf)
     k_mha_fp32<<<grid, QT * KSPLIT, 0, st>>>(Q, ldq, K, ldk, V, ldv, O, ldo, q_start, q_len, k_start, k_len, n_heads,
                                             scale * 1.4426950408889634f);
+    REGTR_CHECK_LAUNCH();
+    return REGTR_OK;
+}
+
+extern "C" int regtr_corr_decode_fwd(const float* Qp, const float* Kp, int ld, const float* xyz, float* out,
+                                     const int32_t* q_start, const int32_t* q_len, const int32_t* k_start,
+                                     const int32_t* k_len, int n_problems, int max_q_len, int n_layers, int n_rows,
+                                     int D, float scale, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (n_problems < 0 || max_q_len < 0 || n_layers < 0 || n_rows < 0 || D <= 0) return REGTR_ERR_ARG;
+    if (D % 4 != 0 || ld % 4 != 0 || ld < D) return REGTR_ERR_UNSUPPORTED;
+    if (n_problems == 0 || max_q_len == 0 || n_layers == 0) return REGTR_OK;
+    if (!Qp || !Kp || !xyz || !out || !q_start || !q_len || !k_start || !k_len) return REGTR_ERR_ARG;
+    if (n_problems > 65535 || n_layers > 65535) return REGTR_ERR_ARG;
+    const size_t smem = ((size_t)D * (CQ + CK) + 4 * CK) * sizeof(float);
+    if (smem > 200 * 1024) return REGTR_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_corr_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -(1000 + (int)e);
+    }
+    dim3 grid(regtr_cdiv(max_q_len, CQ), n_problems, n_layers);
+    k_corr_attention<<<grid, 128, smem, st>>>(Qp, Kp, ld, xyz, out, q_start, q_len, k_start, k_len, n_rows, D,
+                                              scale * 1.4426950408889634f);
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
 }

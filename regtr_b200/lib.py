@@ -49,6 +49,7 @@ SIGNATURES = {
     'regtr_pos_embed_sine': (_I, [_P, _I, _P, _I, _I, _F, _P, _P]),
     'regtr_layernorm_pos': (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P]),
     'regtr_attention_plan': (_I, [_P, _I, _P, _P]),
+    'regtr_corr_decode_fwd': (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
     'regtr_mha_varlen_fwd': (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     'regtr_gemm_tf32x3_qkv_bf16': (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P]),
     'regtr_mha_bf16_tc_fwd': (_I, [_P, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),

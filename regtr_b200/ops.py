@@ -359,6 +359,23 @@ def attention_plan(offs, B: int):
     return plan
 
 
+def corr_decode(qp, kp, xyz, q_start, q_len, k_start, k_len, max_q_len: int, n_layers: int, out=None):
+    """CorrespondenceDecoder.simple_attention for all decoder layers: qp/kp (n_layers*N, D) projected
+    queries / keys, xyz (N,3) -> (n_layers*N, 3) attention-weighted key coordinates."""
+    L = _lib.load()
+    _chk(qp, torch.float32, 'qp', 2); _chk(kp, torch.float32, 'kp', 2); _chk(xyz, torch.float32, 'xyz', 2)
+    rows, D = qp.shape
+    N = xyz.shape[0]
+    if kp.shape != qp.shape or rows != n_layers * N or qp.stride(0) != kp.stride(0) or qp.stride(1) != 1:
+        raise ValueError('corr_decode: inconsistent shapes')
+    out = torch.zeros((rows, 3), dtype=torch.float32, device=qp.device) if out is None else out
+    _lib.check(L.regtr_corr_decode_fwd(_p(qp), _p(kp), qp.stride(0), _p(xyz.contiguous()), _p(out), _p(q_start),
+                                       _p(q_len), _p(k_start), _p(k_len), int(q_start.numel()), int(max_q_len),
+                                       int(n_layers), N, D, 1.0 / math.sqrt(D), _stream()), 'regtr_corr_decode_fwd')
+    _count(1)
+    return out
+
+
 def mha_varlen(q, k, v, q_start, q_len, k_start, k_len, max_q_len: int, n_heads: int, out=None):
     """softmax(q k^T / sqrt(dh)) v per head over explicit (query range, key range) problems.
     q/k/v may be column slices of a wider row-major matrix (stride(0) is the leading dim)."""

@@ -26,8 +26,8 @@ import torch.nn.functional as F
 
 from . import ops
 from .kpconv import KPFEncoder, PreprocessorGPU
-from .transformer import (AttentionPlan, PositionEmbeddingCoordsSine, TransformerCrossEncoder,
-                          TransformerCrossEncoderLayer)
+from .transformer import (AttentionPlan, PositionEmbeddingCoordsSine, PositionEmbeddingLearned,
+                          TransformerCrossEncoder, TransformerCrossEncoderLayer)
 
 
 class _LossParam(nn.Module):
@@ -47,7 +47,7 @@ class CorrespondenceRegressor(nn.Module):
                                       nn.ReLU(), nn.Linear(d_embed, 3))
         self.conf_logits_decoder = nn.Linear(d_embed, 1)
 
-    def forward_packed(self, feats):
+    def forward_packed(self, feats, xyz=None, pe=None, plan=None):
         """feats (L,N,E) packed -> corr (L,N,3), logits (L,N,1)."""
         L_, n, E = feats.shape
         x = feats.reshape(L_ * n, E)
@@ -55,6 +55,39 @@ class CorrespondenceRegressor(nn.Module):
         h = ops.linear(h, self.coor_mlp[2].weight, self.coor_mlp[2].bias, relu=True)
         corr = ops.linear(h, self.coor_mlp[4].weight, self.coor_mlp[4].bias)
         logit = ops.linear(x, self.conf_logits_decoder.weight, self.conf_logits_decoder.bias)
+        return corr.view(L_, n, 3), logit.view(L_, n, 1)
+
+
+class CorrespondenceDecoder(nn.Module):
+    """Attention-based correspondence decoding (regtr.py:297-396, `direct_regress_coor: False`):
+    q_proj / k_proj of the conditioned features (+ position embedding), single-head softmax attention
+    over the OTHER cloud's tokens, values = that cloud's coordinates; overlap logits from the plain
+    features.  Same constructor and state_dict keys (`q_norm` is defined but never applied, as in the
+    reference; `pos_embed` is the shared embedding module).  `num_neighbors > 0` is not supported."""
+
+    def __init__(self, d_embed, use_pos_emb, pos_embed=None, num_neighbors=0):
+        super().__init__()
+        assert use_pos_emb is False or pos_embed is not None, \
+            'Position encoder must be supplied if use_pos_emb is True'
+        if num_neighbors > 0:
+            raise NotImplementedError('top-k neighbour masking is unused by every reference config')
+        self.use_pos_emb = use_pos_emb
+        self.pos_embed = pos_embed
+        self.q_norm = nn.LayerNorm(d_embed)
+        self.q_proj = nn.Linear(d_embed, d_embed)
+        self.k_proj = nn.Linear(d_embed, d_embed)
+        self.conf_logits_decoder = nn.Linear(d_embed, 1)
+        self.num_neighbors = num_neighbors
+
+    def forward_packed(self, feats, xyz, pe, plan: AttentionPlan):
+        """feats (L,N,E) packed, xyz (N,3), pe (N,E) -> corr (L,N,3), logits (L,N,1)."""
+        L_, n, E = feats.shape
+        f2 = (feats + pe[None]) if self.use_pos_emb else feats                      # regtr.py:379-380
+        f2 = f2.reshape(L_ * n, E)
+        qp = ops.linear(f2, self.q_proj.weight, self.q_proj.bias)
+        kp = ops.linear(f2, self.k_proj.weight, self.k_proj.bias)
+        corr = ops.corr_decode(qp, kp, xyz, plan.q_start, plan.q_len, plan.xk_start, plan.xk_len, plan.max_len, L_)
+        logit = ops.linear(feats.reshape(L_ * n, E), self.conf_logits_decoder.weight, self.conf_logits_decoder.bias)
         return corr.view(L_, n, 3), logit.view(L_, n, 1)
 
 
@@ -68,8 +101,10 @@ class RegTR(nn.Module):
         self.feat_proj = nn.Linear(self.kpf_encoder.encoder_skip_dims[-1], cfg.d_embed, bias=True)
         if cfg.get('pos_emb_type', 'sine') == 'sine':
             self.pos_embed = PositionEmbeddingCoordsSine(3, cfg.d_embed, scale=cfg.get('pos_emb_scaling', 1.0))
+        elif cfg['pos_emb_type'] == 'learned':
+            self.pos_embed = PositionEmbeddingLearned(3, cfg.d_embed)
         else:
-            raise NotImplementedError('learned position embedding is a "next" row (SURVEY.md 8f N4)')
+            raise NotImplementedError
         layer = TransformerCrossEncoderLayer(
             cfg.d_embed, cfg.nhead, cfg.d_feedforward, cfg.dropout, activation=cfg.transformer_act,
             normalize_before=cfg.pre_norm, sa_val_has_pos_emb=cfg.sa_val_has_pos_emb,
@@ -81,7 +116,8 @@ class RegTR(nn.Module):
         if cfg.get('direct_regress_coor', False):
             self.correspondence_decoder = CorrespondenceRegressor(cfg.d_embed)
         else:
-            raise NotImplementedError('CorrespondenceDecoder (attention decoding) is a "next" row (SURVEY.md 8f N4)')
+            self.correspondence_decoder = CorrespondenceDecoder(cfg.d_embed, cfg.corr_decoder_has_pos_emb,
+                                                                self.pos_embed)
         if cfg.feature_loss_type == 'infonce':
             self.feature_criterion = _LossParam(cfg.d_embed)
             self.feature_criterion_un = _LossParam(cfg.d_embed)
@@ -103,7 +139,7 @@ class RegTR(nn.Module):
         pe = self.pos_embed(xyz_c)                                                 # regtr.py:149-154
         cond = self.transformer_encoder.forward_packed(
             both_un.contiguous(), pe if cfg.transformer_encoder_has_pos_emb else None, plan)   # (L,N,E)
-        corr, logit = self.correspondence_decoder.forward_packed(cond)             # regtr.py:168-171
+        corr, logit = self.correspondence_decoder.forward_packed(cond, xyz_c, pe, plan)   # regtr.py:168-171
         # correspondences + sigmoid + weighted Kabsch, one launch (regtr.py:185-203)
         pose = ops.pose_from_corr(xyz_c, corr.contiguous(), logit[..., 0].contiguous(), meta['_offs'][-1], B)
         return dict(both_un=both_un, xyz_c=xyz_c, cond=cond, corr=corr, logit=logit, pose=pose)

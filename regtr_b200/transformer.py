@@ -3,7 +3,9 @@
 Host-side mirror of /root/reference/src/models/transformer/{transformers.py,
 position_embedding.py} for the branches both configs select: pre-norm
 `TransformerCrossEncoderLayer.forward_pre` (transformers.py:183-244), `TransformerCrossEncoder`
-with `return_intermediate` + final norm (18-59) and `PositionEmbeddingCoordsSine` (7-50).
+with `return_intermediate` + final norm (18-59) and `PositionEmbeddingCoordsSine` (7-50) -- plus
+the alternative branches of SURVEY.md 8f N4: `forward_post` (121-181) and
+`PositionEmbeddingLearned` (position_embedding.py:53-72).
 Same constructor signatures and state_dict keys (`self_attn.in_proj_weight`, ...).
 
 Design: the reference pads every cloud to the longest one ((L,B,D) tensors + key-padding
@@ -40,6 +42,38 @@ class PositionEmbeddingCoordsSine(nn.Module):
         out = ops.pos_embed_sine(xyz.reshape(-1, self.n_dim).contiguous(), self.d_model, self.temperature,
                                  self.scale_arg)
         return out.reshape(*lead, self.d_model)
+
+
+class PositionEmbeddingLearned(nn.Module):
+    """position_embedding.py:53-72: MLP n_dim -> 32 -> 64 -> 128 -> 256 -> d_model with ReLUs (same
+    constructor and `mlp.{0,2,4,6,8}` state_dict keys); every layer runs on the library GEMM."""
+
+    def __init__(self, n_dim: int = 1, d_model: int = 256):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(n_dim, 32), nn.ReLU(), nn.Linear(32, 64), nn.ReLU(),
+                                 nn.Linear(64, 128), nn.ReLU(), nn.Linear(128, 256), nn.ReLU(),
+                                 nn.Linear(256, d_model))
+
+    def forward(self, xyz: Tensor) -> Tensor:
+        lead = xyz.shape[:-1]
+        x = xyz.reshape(-1, xyz.shape[-1])
+        first = self.mlp[0]
+        pad = (-x.shape[1]) % 4                 # the tensor-core GEMM needs a 16-byte row pitch: zero-pad K
+        if pad:
+            w = first.weight
+            cache = self.__dict__.setdefault('_padded_w', {})
+            key = (w._version, w.data_ptr())
+            if key not in cache:
+                cache.clear()
+                cache[key] = F.pad(w.detach(), (0, pad)).contiguous()
+            x, w0 = F.pad(x, (0, pad)).contiguous(), cache[key]
+        else:
+            x, w0 = x.contiguous(), first.weight
+        h = ops.linear(x, w0, first.bias, relu=True)
+        for i in (2, 4, 6):
+            h = ops.linear(h, self.mlp[i].weight, self.mlp[i].bias, relu=True)
+        h = ops.linear(h, self.mlp[8].weight, self.mlp[8].bias)
+        return h.reshape(*lead, -1)
 
 
 class _MHAParams(nn.Module):
@@ -91,8 +125,6 @@ class TransformerCrossEncoderLayer(nn.Module):
         self.attention_impl = attention_impl
         if attention_type != 'dot_prod':
             raise NotImplementedError
-        if not normalize_before:
-            raise NotImplementedError('forward_post is outside the hot path (both configs use pre_norm)')
         if activation != 'relu':
             raise NotImplementedError('only relu is on the hot path')
         if dropout != 0.0:
@@ -128,6 +160,8 @@ class TransformerCrossEncoderLayer(nn.Module):
 
     def forward_packed(self, x, pos, plan: AttentionPlan):
         """x, pos: (N,E) packed tokens (src clouds then tgt clouds).  Returns updated x."""
+        if not self.normalize_before:
+            return self.forward_post_packed(x, pos, plan)
         has_pos = pos is not None
         # self attention (shared weights for src and tgt: one launch over all 2B clouds)
         x2, x2p = ops.layernorm_pos(x, self.norm1.weight, self.norm1.bias, pos, self.norm1.eps,
@@ -144,6 +178,25 @@ class TransformerCrossEncoderLayer(nn.Module):
                                   want_plain=True, want_pos=False)
         h = ops.linear(x2, self.linear1.weight, self.linear1.bias, relu=True)
         x = ops.linear(h, self.linear2.weight, self.linear2.bias, residual=x)
+        return x
+
+
+    def forward_post_packed(self, x, pos, plan: AttentionPlan):
+        """Post-norm layer (transformers.py:121-181): attention on x (+pos), then LayerNorm(x + update)."""
+        has_pos = pos is not None
+        ln = lambda y, norm, want_pos: ops.layernorm_pos(y, norm.weight, norm.bias, pos if want_pos else None,
+                                                         norm.eps, want_plain=True, want_pos=want_pos and has_pos)
+        xp = x + pos if has_pos else x
+        o = self._attend(self.self_attn, x, xp, self.sa_val_has_pos_emb or not has_pos, plan, cross=False)
+        y = ops.linear(o, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, residual=x)
+        x, xp = ln(y, self.norm1, True)
+        xp = xp if has_pos else x
+        o = self._attend(self.multihead_attn, x, xp, self.ca_val_has_pos_emb or not has_pos, plan, cross=True)
+        y = ops.linear(o, self.multihead_attn.out_proj.weight, self.multihead_attn.out_proj.bias, residual=x)
+        x, _ = ln(y, self.norm2, False)
+        h = ops.linear(x, self.linear1.weight, self.linear1.bias, relu=True)
+        y = ops.linear(h, self.linear2.weight, self.linear2.bias, residual=x)
+        x, _ = ln(y, self.norm3, False)
         return x
 
 

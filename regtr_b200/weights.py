@@ -79,8 +79,15 @@ def state_dict_spec(cfg):
         for n in ('norm1', 'norm2', 'norm3'):
             spec[pre + n + '.weight'] = (E,)
             spec[pre + n + '.bias'] = (E,)
-    spec['transformer_encoder.norm.weight'] = (E,)
-    spec['transformer_encoder.norm.bias'] = (E,)
+    if cfg.pre_norm:                                      # regtr.py:64: final norm only for pre-norm stacks
+        spec['transformer_encoder.norm.weight'] = (E,)
+        spec['transformer_encoder.norm.bias'] = (E,)
+    learned = cfg.get('pos_emb_type', 'sine') == 'learned'
+    pe_dims = [(32, 3), (64, 32), (128, 64), (256, 128), (E, 256)]   # position_embedding.py:59-69
+    if learned:
+        for i, (o, k) in zip((0, 2, 4, 6, 8), pe_dims):
+            spec[f'pos_embed.mlp.{i}.weight'] = (o, k)
+            spec[f'pos_embed.mlp.{i}.bias'] = (o,)
     if cfg.get('direct_regress_coor', False):
         pre = 'correspondence_decoder.'
         spec[pre + 'coor_mlp.0.weight'] = (E, E); spec[pre + 'coor_mlp.0.bias'] = (E,)
@@ -88,8 +95,17 @@ def state_dict_spec(cfg):
         spec[pre + 'coor_mlp.4.weight'] = (3, E); spec[pre + 'coor_mlp.4.bias'] = (3,)
         spec[pre + 'conf_logits_decoder.weight'] = (1, E)
         spec[pre + 'conf_logits_decoder.bias'] = (1,)
-    else:
-        raise NotImplementedError('CorrespondenceDecoder is a "next" row (SURVEY.md 8f N4)')
+    else:                                                 # CorrespondenceDecoder (regtr.py:298-311)
+        pre = 'correspondence_decoder.'
+        if learned:                                       # the shared embedding module is registered twice
+            for i, (o, k) in zip((0, 2, 4, 6, 8), pe_dims):
+                spec[pre + f'pos_embed.mlp.{i}.weight'] = (o, k)
+                spec[pre + f'pos_embed.mlp.{i}.bias'] = (o,)
+        spec[pre + 'q_norm.weight'] = (E,); spec[pre + 'q_norm.bias'] = (E,)
+        spec[pre + 'q_proj.weight'] = (E, E); spec[pre + 'q_proj.bias'] = (E,)
+        spec[pre + 'k_proj.weight'] = (E, E); spec[pre + 'k_proj.bias'] = (E,)
+        spec[pre + 'conf_logits_decoder.weight'] = (1, E)
+        spec[pre + 'conf_logits_decoder.bias'] = (1,)
     if cfg.feature_loss_type == 'infonce':
         spec['feature_criterion.W'] = (E, E)
         spec['feature_criterion_un.W'] = (E, E)
@@ -114,9 +130,9 @@ def random_state_dict(cfg, seed: int = 0, spread_corr: bool = True):
         elif key.endswith('KPConv.weights'):
             bound = 1.0 / math.sqrt(shape[1] * shape[2])
             arr = rng.uniform(-bound, bound, size=shape)
-        elif '.norm' in key and key.endswith('weight'):
+        elif ('.norm' in key or 'q_norm' in key) and key.endswith('weight'):
             arr = 1.0 + 0.1 * rng.standard_normal(shape)
-        elif '.norm' in key and key.endswith('bias'):
+        elif ('.norm' in key or 'q_norm' in key) and key.endswith('bias'):
             arr = 0.1 * rng.standard_normal(shape)
         elif key.endswith('.W'):
             arr = np.eye(shape[0])
@@ -130,4 +146,7 @@ def random_state_dict(cfg, seed: int = 0, spread_corr: bool = True):
             if spread_corr and key.endswith('conf_logits_decoder.weight'):
                 arr = arr * 4.0
         sd[key] = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32))
+    for key in list(sd):                                  # one module, two names: same tensors
+        if key.startswith('correspondence_decoder.pos_embed.'):
+            sd[key] = sd[key[len('correspondence_decoder.'):]]
     return sd

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import FORWARD_CASES, check_forward_against_golden, load_golden, make_case
+from conftest import FORWARD_CASES, VARIANT_CASES, check_forward_against_golden, load_golden, make_case
 
 pytestmark = pytest.mark.gpu
 
@@ -218,6 +218,56 @@ def test_forward_vs_reference_golden(case):
     assert out['pose'].shape == (6, len(src), 3, 4)
     check_forward_against_golden(out, meta, load_golden(case), len(src), feat_rtol=1e-4, corr_atol=1e-4,
                                  logit_atol=2e-4, pose_atol=1e-4)
+
+
+@pytest.mark.parametrize('case', sorted(VARIANT_CASES))
+def test_variant_forward_vs_reference_golden(case):
+    """SURVEY.md 8f N4 branches on the CUDA path: CorrespondenceDecoder (regtr_corr_decode_fwd), forward_post,
+    PositionEmbeddingLearned -- against the unmodified reference run with the same config and weights."""
+    cfg, sd, src, tgt = make_case(case)
+    out, meta = _run_model(cfg, sd, src, tgt)
+    check_forward_against_golden(out, meta, load_golden(case), len(src), feat_rtol=1e-4, corr_atol=1e-4,
+                                 logit_atol=2e-4, pose_atol=1e-4)
+
+
+def test_variant_forward_through_graph_executor():
+    """The attention decoder + learned embedding also run capacity-shaped inside a CUDA graph."""
+    from regtr_b200.regtr import GraphedRegTR, RegTR
+    case = 'var_modelnet_learnedpe_attndec_b2'
+    cfg, sd, src, tgt = make_case(case)
+    model = RegTR(cfg).to(DEV).eval()
+    model.load_state_dict(sd, strict=True)
+    # ModelNet's single subsampling step keeps ~85 % of the points: level capacities = level-0 capacity
+    runner = GraphedRegTR(model, bucket=2048, ratio=1.0)
+    batch = {'src_xyz': [G(a) for a in src], 'tgt_xyz': [G(a) for a in tgt]}
+    out = runner(batch)
+    check_forward_against_golden(out, batch['kpconv_meta'], load_golden(case), len(src), feat_rtol=1e-4,
+                                 corr_atol=1e-4, logit_atol=2e-4, pose_atol=1e-4)
+    assert runner.fallbacks == 0
+
+
+def test_corr_decode_vs_float64():
+    """regtr_corr_decode_fwd alone: ragged problems, several layers, vs a float64 softmax-attention."""
+    from regtr_b200 import ops
+    from regtr_b200.transformer import AttentionPlan
+    rng = np.random.default_rng(3)
+    lens, L_, D = [37, 1, 50, 129], 3, 256
+    n = sum(lens)
+    qp = G(rng.normal(size=(L_ * n, D)).astype(np.float32))
+    kp = G(rng.normal(size=(L_ * n, D)).astype(np.float32))
+    xyz = G(rng.normal(size=(n, 3)).astype(np.float32))
+    plan = AttentionPlan(lens, DEV)
+    got = N(ops.corr_decode(qp, kp, xyz, plan.q_start, plan.q_len, plan.xk_start, plan.xk_len, plan.max_len, L_))
+    starts = np.concatenate([[0], np.cumsum(lens)])
+    B = len(lens) // 2
+    q64, k64, x64 = N(qp).astype(np.float64).reshape(L_, n, D), N(kp).astype(np.float64).reshape(L_, n, D), N(xyz).astype(np.float64)
+    for c in range(len(lens)):
+        o = c + B if c < B else c - B
+        qs, ks = slice(starts[c], starts[c + 1]), slice(starts[o], starts[o + 1])
+        for l in range(L_):
+            sc = q64[l, qs] @ k64[l, ks].T / np.sqrt(D)
+            w = np.exp(sc - sc.max(1, keepdims=True)); w /= w.sum(1, keepdims=True)
+            np.testing.assert_allclose(got.reshape(L_, n, 3)[l, qs], w @ x64[ks], rtol=0, atol=2e-5)
 
 
 def test_forward_3dmatch_full_size_vs_oracle():

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import FORWARD_CASES, check_forward_against_golden, load_golden, make_case
+from conftest import FORWARD_CASES, VARIANT_CASES, check_forward_against_golden, load_golden, make_case
 from oracle import pre, regtr_oracle as O
 
 
@@ -56,6 +56,17 @@ def test_forward_matches_reference(case):
     out = O.forward(sd, cfg, src, tgt)
     check_forward_against_golden(out, out['kpconv_meta'], fx, len(src), feat_rtol=2e-5, corr_atol=3e-5,
                                  logit_atol=5e-5, pose_atol=1e-4)   # north_star: pose within 1e-4
+
+
+@pytest.mark.parametrize('case', sorted(VARIANT_CASES))
+def test_variant_forward_matches_reference(case):
+    """Alternative config branches: attention-based CorrespondenceDecoder, post-norm
+    layers, learned position embedding -- oracle vs the unmodified reference run with that config."""
+    cfg, sd, src, tgt = make_case(case)
+    fx = load_golden(case)
+    out = O.forward(sd, cfg, src, tgt)
+    check_forward_against_golden(out, out['kpconv_meta'], fx, len(src), feat_rtol=2e-5, corr_atol=3e-5,
+                                 logit_atol=5e-5, pose_atol=1e-4)
 
 
 def test_c_preprocess_matches_numpy_twin():
