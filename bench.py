@@ -398,35 +398,45 @@ def main():
         # by launch on its own stream: [L2 flush][event][kernel][event], 3 repetitions each, over the
         # 11 KPConv calls of the last traced step.  The flush (~80 us) hides the launch latency.
         last = tr[-11:] if len(tr) >= 11 else tr
-        gather_ms = 0.0
+        gather_ms = warm_ms = 0.0
         per_launch = []
         for _, _, info in last:
-            best = None
+            best = best_w = None
             for _ in range(3):
                 flush.zero_()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                ops.kpconv_aggregate(*info['args'], row_flags=info.get('row_flags'))
-                e1.record()
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                ev[0].record()
+                ops.kpconv_aggregate(*info['args'], row_flags=info.get('row_flags'))      # cold: L2 just flushed
+                ev[1].record()
+                ev[2].record()
+                ops.kpconv_aggregate(*info['args'], row_flags=info.get('row_flags'))      # inputs L2-resident, as
+                ev[3].record()                                                            # behind their producer
                 torch.cuda.synchronize()
-                t = e0.elapsed_time(e1)
+                t, tw = ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3])
                 best = t if best is None else min(best, t)
+                best_w = tw if best_w is None else min(best_w, tw)
             gather_ms += best
-            per_launch.append(dict(Nq=info['Nq'], Cin=info['Cin'], us=round(best * 1e3, 1)))
+            warm_ms += best_w
+            per_launch.append(dict(Nq=info['Nq'], Cin=info['Cin'], us=round(best * 1e3, 1),
+                                   us_l2_warm=round(best_w * 1e3, 1)))
         tot_ms = sum(a.elapsed_time(b) for a, b, _ in tr) / nsteps          # whole KPConv op incl. weight GEMM (eager)
         step_bytes = sum(kpconv_algorithmic_bytes(info) for _, _, info in last)
         peak, peak_src = peaks()
         ach = step_bytes / (gather_ms * 1e-3) / 1e9
         roof = dict(bound='hbm',
-                    kernel='k_kpconv_agg (+k_row_flags where the flags are not fused upstream): KPConv neighbour gather + kernel-point influence + '
-                           'aggregation, 11 launches/pair; bytes = SURVEY 8d algorithmic bytes of the KPConv op',
+                    kernel='k_kpconv_agg_mma / k_kpconv_c1 (+k_row_flags where the flags are not fused upstream): KPConv neighbour '
+                           'gather + kernel-point influence + aggregation, 11 launches/pair, each timed alone right after '
+                           'an L2 flush; bytes = SURVEY 8d algorithmic bytes of the KPConv op',
                     achieved=ach, peak=peak, unit='GB/s', frac=ach / peak,
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 11 launches of one
-                    # `ncu --set full` capture of this workload (profiles/r01_ncu_kpconv_agg_summary.csv):
-                    # 58.5 MB per pair against 590 MB algorithmic -- the 126 MB L2 absorbs the row reuse
-                    traffic=58.5e6 / 11, traffic_unit='bytes/launch (ncu capture, batch 1)', peak_source=peak_src,
+                    # `ncu --set full` capture of this workload (profiles/r01_ncu_kpconv_agg_mma_summary.csv):
+                    # 55.5 MB per pair against 590 MB algorithmic -- the 126 MB L2 absorbs the row reuse
+                    traffic=55.5e6 / 11, traffic_unit='bytes/launch (ncu capture, batch 1)', peak_source=peak_src,
                     algorithmic_bytes_per_launch=step_bytes / max(len(last), 1),
                     algorithmic_bytes_per_step=step_bytes, gather_ms_per_step=gather_ms,
+                    # the same launches with their inputs still in L2 (the state behind the producer kernel
+                    # inside a forward); `achieved`/`frac` above are the conservative cold-L2 figures
+                    gather_ms_per_step_l2_warm=warm_ms, frac_l2_warm=step_bytes / (warm_ms * 1e-3) / 1e9 / peak,
                     kpconv_op_ms_per_step_eager=tot_ms, per_launch=per_launch)
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only)
@@ -457,7 +467,7 @@ def main():
             dtype='f32', data='synthetic',
             config=dict(workload=workload_name(args, B), pairs_per_gpu_per_step=B,
                         parallelism=f'pair-level data parallel x{world}', l2_flush_between_steps=True,
-                        weights='seeded random init (no pretrained weights offline)', precision_mode='fp32 parity (3xTF32 tcgen05 GEMMs, fp32 attention)' if args.attention == 'fp32'
+                        weights='seeded random init (no pretrained weights offline)', precision_mode='fp32 parity (3xTF32 tcgen05 GEMMs, 3xTF32 mma.sync attention + KPConv aggregation)' if args.attention == 'fp32'
                         else 'fast (3xTF32 GEMMs, bf16 tcgen05 attention core)',
                         executor=(f'cuda-graph, {depth} pairs in flight (PipelinedRegTR)' if depth > 1 else
                                   'cuda-graph (GraphedRegTR)') if args.graph else 'eager',

@@ -40,10 +40,14 @@ def test_kpconv_vs_reference_golden(ops_golden):
     assert np.all(N(y)[3] == 0)
 
 
-@pytest.mark.parametrize('cin,cout', [(1, 64), (32, 32), (64, 64), (128, 128), (256, 256)])
-def test_kpconv_all_channel_paths_vs_oracle(cin, cout):
+@pytest.mark.parametrize('impl', ['mma', 'ffma'])
+@pytest.mark.parametrize('cin,cout', [(1, 64), (4, 16), (32, 32), (64, 64), (128, 128), (256, 256)])
+def test_kpconv_all_channel_paths_vs_oracle(cin, cout, impl, monkeypatch):
+    """Both aggregation implementations (tensor-core mma.sync, the default, and the CUDA-core kernels kept
+    for A/B and as the large-K fallback) on every channel-width path, incl. the fused Cin=1 block."""
     from oracle import regtr_oracle as O
     from regtr_b200 import ops
+    monkeypatch.setenv('REGTR_AGG_IMPL', impl)
     rng = np.random.default_rng(cin)
     Nq, Ns, K = 301, 457, 40
     q = rng.normal(size=(Nq, 3)).astype(np.float32) * 0.05
@@ -244,6 +248,35 @@ def test_variant_forward_through_graph_executor():
     check_forward_against_golden(out, batch['kpconv_meta'], load_golden(case), len(src), feat_rtol=1e-4,
                                  corr_atol=1e-4, logit_atol=2e-4, pose_atol=1e-4)
     assert runner.fallbacks == 0
+
+
+def test_attention_cores_agree_and_match_float64(monkeypatch):
+    """The fp32-accurate attention cores (mma.sync 3xTF32 default, CUDA-core REGTR_MHA_IMPL=ffma) on ragged
+    self and cross problems, incl. a 1-token cloud and lengths around the 64-key chunk."""
+    from regtr_b200 import ops
+    from regtr_b200.transformer import AttentionPlan
+    rng = np.random.default_rng(11)
+    lens, E, H = [130, 1, 64, 65, 3, 200], 256, 8
+    n = sum(lens)
+    q, k, v = (G((rng.normal(size=(n, E)) * 0.7).astype(np.float32)) for _ in range(3))
+    plan = AttentionPlan(lens, DEV)
+    starts = np.concatenate([[0], np.cumsum(lens)])
+    B = len(lens) // 2
+    for cross in (False, True):
+        ks, kl = (plan.xk_start, plan.xk_len) if cross else (plan.q_start, plan.q_len)
+        ref = np.zeros((n, E))
+        for c in range(len(lens)):
+            o = (c + B if c < B else c - B) if cross else c
+            qq = N(q)[starts[c]:starts[c + 1]].astype(np.float64).reshape(-1, H, 32).transpose(1, 0, 2)
+            kk = N(k)[starts[o]:starts[o + 1]].astype(np.float64).reshape(-1, H, 32).transpose(1, 0, 2)
+            vv = N(v)[starts[o]:starts[o + 1]].astype(np.float64).reshape(-1, H, 32).transpose(1, 0, 2)
+            sc = qq @ kk.transpose(0, 2, 1) / np.sqrt(32)
+            w = np.exp(sc - sc.max(-1, keepdims=True)); w /= w.sum(-1, keepdims=True)
+            ref[starts[c]:starts[c + 1]] = (w @ vv).transpose(1, 0, 2).reshape(-1, E)
+        for impl in ('mma', 'ffma'):
+            monkeypatch.setenv('REGTR_MHA_IMPL', impl)
+            got = N(ops.mha_varlen(q, k, v, plan.q_start, plan.q_len, ks, kl, plan.max_len, H))
+            assert np.abs(got - ref).max() <= 1e-5, (impl, cross)
 
 
 def test_corr_decode_vs_float64():
