@@ -156,9 +156,10 @@ int regtr_pos_embed_sine(const float* xyz, int n, const float* dim_t, int n_freq
 
 /* LayerNorm over the last dim with optional position add:  y = LN(x)*g + b ;
  * y_pos = y + pos.  Replaces nn.LayerNorm + with_pos_embed (transformers.py:117-119,
- * 194-196, 213-215, 232).  Any of y / y_pos may be NULL. */
+ * 194-196, 213-215, 232).  Any of y / y_pos may be NULL.  n_dev (optional, device): the real row count
+ * when n is a capacity; rows beyond it are left untouched. */
 int regtr_layernorm_pos(const float* x, const float* gamma, const float* beta, const float* pos,
-                        int n, int E, float eps, float* y, float* y_pos, void* stream);
+                        int n, const int32_t* n_dev, int E, float eps, float* y, float* y_pos, void* stream);
 
 /* Device-side attention problem table for a (src x B, tgt x B) token stack with cloud offsets
  * offs (2B+1): plan (4, 2B) i32 rows = q_start, q_len, cross k_start, cross k_len (the cross

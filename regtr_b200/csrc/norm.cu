@@ -139,9 +139,11 @@ __global__ void k_in_apply(const float* x, const int32_t* __restrict__ offs, int
 
 // One warp per row; E <= 1024, multiple of 32.
 __global__ void k_layernorm_pos(const float* __restrict__ x, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, const float* __restrict__ pos, int n, int E,
-                                float eps, float* __restrict__ y, float* __restrict__ y_pos) {
+                                const float* __restrict__ beta, const float* __restrict__ pos, int n,
+                                const int32_t* __restrict__ n_dev, int E, float eps, float* __restrict__ y,
+                                float* __restrict__ y_pos) {
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (n_dev) n = min(n, *n_dev);               // capacity-shaped launch: rows beyond the real count are skipped
     if (row >= n) return;
     const float* xr = x + (size_t)row * E;
     float v[32];
@@ -220,13 +222,13 @@ int regtr_instnorm_act(const float* x, const int32_t* offs, int n_clouds, int n_
     return REGTR_OK;
 }
 
-int regtr_layernorm_pos(const float* x, const float* gamma, const float* beta, const float* pos, int n, int E,
-                        float eps, float* y, float* y_pos, void* stream_) {
+int regtr_layernorm_pos(const float* x, const float* gamma, const float* beta, const float* pos, int n,
+                        const int32_t* n_dev, int E, float eps, float* y, float* y_pos, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (n < 0 || E <= 0 || E % 32 != 0 || E > 1024) return REGTR_ERR_ARG;
     if (n == 0) return REGTR_OK;
     if (!x || !gamma || !beta || (!y && !y_pos)) return REGTR_ERR_ARG;
-    k_layernorm_pos<<<regtr_cdiv((long long)n * 32, 256), 256, 0, st>>>(x, gamma, beta, pos, n, E, eps, y, y_pos);
+    k_layernorm_pos<<<regtr_cdiv((long long)n * 32, 256), 256, 0, st>>>(x, gamma, beta, pos, n, n_dev, E, eps, y, y_pos);
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
 }

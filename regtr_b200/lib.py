@@ -47,7 +47,7 @@ SIGNATURES = {
     'regtr_gemm_ws_bytes': (_Z, [_I, _I, _I]),
     'regtr_gemm_tf32x3': (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _Z, _P]),
     'regtr_pos_embed_sine': (_I, [_P, _I, _P, _I, _I, _F, _P, _P]),
-    'regtr_layernorm_pos': (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P]),
+    'regtr_layernorm_pos': (_I, [_P, _P, _P, _P, _I, _P, _I, _F, _P, _P, _P]),
     'regtr_attention_plan': (_I, [_P, _I, _P, _P]),
     'regtr_corr_decode_fwd': (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
     'regtr_mha_varlen_fwd': (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),

@@ -334,8 +334,8 @@ def pos_embed_sine(xyz, d_model: int = 256, temperature: float = 10000.0, scale:
     return out
 
 
-def layernorm_pos(x, gamma, beta, pos=None, eps: float = 1e-5, want_plain=True, want_pos=True):
-    """-> (LN(x), LN(x)+pos); either may be skipped."""
+def layernorm_pos(x, gamma, beta, pos=None, eps: float = 1e-5, want_plain=True, want_pos=True, n_dev=None):
+    """-> (LN(x), LN(x)+pos); either may be skipped.  n_dev: device row count when x is capacity-shaped."""
     L = _lib.load()
     _chk(x, torch.float32, 'x', 2)
     n, E = x.shape
@@ -343,8 +343,8 @@ def layernorm_pos(x, gamma, beta, pos=None, eps: float = 1e-5, want_plain=True, 
     yp = torch.empty_like(x) if want_pos else None
     if 'ln' in _ABLATE:
         return (y.copy_(x) if y is not None else None), (yp.copy_(x) if yp is not None else None)
-    _lib.check(L.regtr_layernorm_pos(_p(x), _p(gamma), _p(beta), _p(pos), n, E, float(eps), _p(y), _p(yp), _stream()),
-               'regtr_layernorm_pos')
+    _lib.check(L.regtr_layernorm_pos(_p(x), _p(gamma), _p(beta), _p(pos), n, _p(n_dev), E, float(eps), _p(y), _p(yp),
+                                     _stream()), 'regtr_layernorm_pos')
     _count(1)
     return y, yp
 

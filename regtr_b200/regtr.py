@@ -134,7 +134,9 @@ class RegTR(nn.Module):
         pts = meta['_points']
         feats0 = torch.ones_like(pts[0][:, 0:1])                                   # regtr.py:122
         feats_un, _ = self.kpf_encoder(feats0, meta)                               # regtr.py:136
-        both_un = ops.linear(feats_un, self.feat_proj.weight, self.feat_proj.bias)  # regtr.py:145
+        nd = meta.get('_ndev')
+        both_un = ops.linear(feats_un, self.feat_proj.weight, self.feat_proj.bias,
+                             m_dev=nd[-1] if nd else None)                         # regtr.py:145
         xyz_c = pts[-1]
         pe = self.pos_embed(xyz_c)                                                 # regtr.py:149-154
         cond = self.transformer_encoder.forward_packed(

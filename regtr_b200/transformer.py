@@ -92,9 +92,11 @@ class _MHAParams(nn.Module):
 class AttentionPlan:
     """Device-side (start,len) tables of the self and cross attention problems of a batch:
     problem c = cloud c of the (src x B, tgt x B) stack; its cross partner is the other cloud of
-    the pair.  `max_len` is a host-side upper bound of the sequence lengths (grid sizing only)."""
+    the pair.  `max_len` is a host-side upper bound of the sequence lengths (grid sizing only);
+    `n_dev` (static-shape pipelines only) is the device-side total token count, so that the dense
+    layers skip the capacity padding rows."""
 
-    def __init__(self, lens=None, device=None, table=None, max_len=None):
+    def __init__(self, lens=None, device=None, table=None, max_len=None, n_dev=None):
         if table is None:
             n2 = len(lens)
             B = n2 // 2
@@ -108,11 +110,12 @@ class AttentionPlan:
             max_len = max(map(int, lens)) if n2 else 0
         self.q_start, self.q_len, self.xk_start, self.xk_len = table[0], table[1], table[2], table[3]
         self.max_len = int(max_len)
+        self.n_dev = n_dev
 
     @classmethod
     def from_device(cls, offs, B: int, max_len: int):
         """Sync-free construction from device offsets (static-shape / CUDA-graph pipelines)."""
-        return cls(table=ops.attention_plan(offs, B), max_len=max_len)
+        return cls(table=ops.attention_plan(offs, B), max_len=max_len, n_dev=offs[2 * B:2 * B + 1])
 
 
 class TransformerCrossEncoderLayer(nn.Module):
@@ -148,13 +151,14 @@ class TransformerCrossEncoderLayer(nn.Module):
         if self.attention_impl == 'bf16_tc' and val_has_pos:
             # fast mode: in-projection with a bf16 epilogue + tcgen05 attention core (TMA-fed, TMEM accumulators)
             return ops.mha_bf16_tc(x2p, W, b, plan.q_start, plan.q_len, ks, kl, plan.max_len, self.nhead)
+        nd = plan.n_dev
         if val_has_pos:
-            qkv = ops.linear(x2p, W, b)                   # one packed in-projection GEMM
+            qkv = ops.linear(x2p, W, b, m_dev=nd)         # one packed in-projection GEMM
             q, k, v = qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:]
         else:
-            qk = ops.linear(x2p, W[:2 * E], b[:2 * E])
+            qk = ops.linear(x2p, W[:2 * E], b[:2 * E], m_dev=nd)
             q, k = qk[:, :E], qk[:, E:]
-            v = ops.linear(x2, W[2 * E:], b[2 * E:])
+            v = ops.linear(x2, W[2 * E:], b[2 * E:], m_dev=nd)
         o = ops.mha_varlen(q, k, v, plan.q_start, plan.q_len, ks, kl, plan.max_len, self.nhead)
         return o
 
@@ -163,39 +167,42 @@ class TransformerCrossEncoderLayer(nn.Module):
         if not self.normalize_before:
             return self.forward_post_packed(x, pos, plan)
         has_pos = pos is not None
+        nd = plan.n_dev
         # self attention (shared weights for src and tgt: one launch over all 2B clouds)
         x2, x2p = ops.layernorm_pos(x, self.norm1.weight, self.norm1.bias, pos, self.norm1.eps,
-                                    want_plain=not self.sa_val_has_pos_emb, want_pos=True)
+                                    want_plain=not self.sa_val_has_pos_emb, want_pos=True, n_dev=nd)
         o = self._attend(self.self_attn, x2, x2p, self.sa_val_has_pos_emb or not has_pos, plan, cross=False)
-        x = ops.linear(o, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, residual=x)
+        x = ops.linear(o, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, residual=x, m_dev=nd)
         # cross attention, both directions from the same pre-update normalised features
         x2, x2p = ops.layernorm_pos(x, self.norm2.weight, self.norm2.bias, pos, self.norm2.eps,
-                                    want_plain=not self.ca_val_has_pos_emb, want_pos=True)
+                                    want_plain=not self.ca_val_has_pos_emb, want_pos=True, n_dev=nd)
         o = self._attend(self.multihead_attn, x2, x2p, self.ca_val_has_pos_emb or not has_pos, plan, cross=True)
-        x = ops.linear(o, self.multihead_attn.out_proj.weight, self.multihead_attn.out_proj.bias, residual=x)
+        x = ops.linear(o, self.multihead_attn.out_proj.weight, self.multihead_attn.out_proj.bias, residual=x, m_dev=nd)
         # position-wise feed-forward
         x2, _ = ops.layernorm_pos(x, self.norm3.weight, self.norm3.bias, None, self.norm3.eps,
-                                  want_plain=True, want_pos=False)
-        h = ops.linear(x2, self.linear1.weight, self.linear1.bias, relu=True)
-        x = ops.linear(h, self.linear2.weight, self.linear2.bias, residual=x)
+                                  want_plain=True, want_pos=False, n_dev=nd)
+        h = ops.linear(x2, self.linear1.weight, self.linear1.bias, relu=True, m_dev=nd)
+        x = ops.linear(h, self.linear2.weight, self.linear2.bias, residual=x, m_dev=nd)
         return x
 
 
     def forward_post_packed(self, x, pos, plan: AttentionPlan):
         """Post-norm layer (transformers.py:121-181): attention on x (+pos), then LayerNorm(x + update)."""
         has_pos = pos is not None
+        nd = plan.n_dev
         ln = lambda y, norm, want_pos: ops.layernorm_pos(y, norm.weight, norm.bias, pos if want_pos else None,
-                                                         norm.eps, want_plain=True, want_pos=want_pos and has_pos)
+                                                         norm.eps, want_plain=True, want_pos=want_pos and has_pos,
+                                                         n_dev=nd)
         xp = x + pos if has_pos else x
         o = self._attend(self.self_attn, x, xp, self.sa_val_has_pos_emb or not has_pos, plan, cross=False)
-        y = ops.linear(o, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, residual=x)
+        y = ops.linear(o, self.self_attn.out_proj.weight, self.self_attn.out_proj.bias, residual=x, m_dev=nd)
         x, xp = ln(y, self.norm1, True)
         xp = xp if has_pos else x
         o = self._attend(self.multihead_attn, x, xp, self.ca_val_has_pos_emb or not has_pos, plan, cross=True)
-        y = ops.linear(o, self.multihead_attn.out_proj.weight, self.multihead_attn.out_proj.bias, residual=x)
+        y = ops.linear(o, self.multihead_attn.out_proj.weight, self.multihead_attn.out_proj.bias, residual=x, m_dev=nd)
         x, _ = ln(y, self.norm2, False)
-        h = ops.linear(x, self.linear1.weight, self.linear1.bias, relu=True)
-        y = ops.linear(h, self.linear2.weight, self.linear2.bias, residual=x)
+        h = ops.linear(x, self.linear1.weight, self.linear1.bias, relu=True, m_dev=nd)
+        y = ops.linear(h, self.linear2.weight, self.linear2.bias, residual=x, m_dev=nd)
         x, _ = ln(y, self.norm3, False)
         return x
 
@@ -218,15 +225,15 @@ class TransformerCrossEncoder(nn.Module):
         for layer in self.layers:
             x = layer.forward_packed(x, pos, plan)
             if self.return_intermediate:
-                outs.append(self._final(x))
+                outs.append(self._final(x, plan.n_dev))
         if not self.return_intermediate:
-            outs.append(self._final(x))
+            outs.append(self._final(x, plan.n_dev))
         return torch.stack(outs)
 
-    def _final(self, x):
+    def _final(self, x, n_dev=None):
         if self.norm is None:
             return x
-        y, _ = ops.layernorm_pos(x, self.norm.weight, self.norm.bias, None, self.norm.eps, True, False)
+        y, _ = ops.layernorm_pos(x, self.norm.weight, self.norm.bias, None, self.norm.eps, True, False, n_dev=n_dev)
         return y
 
     def forward(self, src, tgt, src_mask: Optional[Tensor] = None, tgt_mask: Optional[Tensor] = None,
