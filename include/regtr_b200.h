@@ -92,7 +92,8 @@ int regtr_ball_query(const float* q, const int32_t* q_offs, const int32_t* q_ord
  * q (Nq,3) s (Ns,3) idx (Nq,K) i32, x (Ns,Cin) f32, W (P,Cin,Cout) f32, kp (P,3), out (Nq,Cout).
  * P must be 15.  Cin in {1..16} or 32/64/128/256.
  * nq_dev / ns_dev (optional, device int32): actual query / support counts when Nq / Ns are
- * capacities (static-shape pipelines); rows >= *nq_dev produce zeros, the shadow index is *ns_dev.
+ * capacities (static-shape pipelines); rows >= *nq_dev are padding (zeroed up to the next multiple of
+ * 128, untouched beyond -- consumers work in 128-row tiles); the shadow index is *ns_dev.
  * ws: regtr_kpconv_ws_bytes(Nq, Ns, Cin) bytes (aggregated features + row flags). */
 size_t regtr_kpconv_ws_bytes(int Nq, int Ns, int Cin);
 int regtr_kpconv_fwd(const float* q, const float* s, const int32_t* idx, const float* x,
@@ -118,7 +119,8 @@ int regtr_max_pool(const float* x, const int32_t* idx, int Nq, int Ns, const int
  * residual add, optional LeakyReLU.  Replaces BatchNormBlock.forward + nn.LeakyReLU
  * (kpconv_blocks.py:497-519, 546-561, 646, 741):  out = act(norm(x) + res).
  * x (n,C); offs (n_clouds+1) i32 device; n_cap >= offs[n_clouds]; res optional (n,C);
- * slope < 0 disables the activation.  In-place (out == x) is allowed.
+ * slope < 0 disables the activation.  In-place (out == x) is allowed.  Rows in [offs[n_clouds], n_cap)
+ * are padding: zeroed up to the next multiple of 128, untouched beyond.
  * rowflag_out (optional, n_cap bytes, C/4 a power of two <= 32): flags[r] = (sum_c out[r,c] > 0),
  * the neighbour-count predicate of the KPConv that consumes `out`. */
 size_t regtr_instnorm_ws_bytes(int n_cap, int n_clouds, int C);

@@ -30,6 +30,11 @@ __global__ void k_row_flags(const float* __restrict__ x, int n, int C, uint8_t* 
     if (lane == 0) flags[warp] = acc > 0.0;
 }
 
+// Capacity-shaped launches: rows at or beyond the real count n are padding.  Their only consumer is a GEMM
+// that works in 128-row tiles, skips tiles beyond n and never stores rows >= n, so padding rows need
+// defined (zero) contents only inside the tile that straddles n; the rest of the capacity is left untouched.
+__device__ __forceinline__ int pad_band_end(int n) { return (n + 127) & ~127; }
+
 // ---- packed fp32x2 FMA (sm_100: one instruction, two FMAs)
 typedef unsigned long long f2;
 __device__ __forceinline__ f2 f2_dup(float x) { f2 r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(x)); return r; }
@@ -109,9 +114,11 @@ k_kpconv_agg(const float* __restrict__ q, const float* __restrict__ s, const int
     const int qi = blockIdx.x * AGG_WARPS + warp;
     if (qi >= Nq) return;
     if (ns_dev) Ns = min(Ns, *ns_dev);
-    if (nq_dev && qi >= *nq_dev) {               // capacity padding row: zeros
-        float* o = wf + (size_t)qi * (KP * CIN);
-        for (int t = lane; t < KP * CIN; t += 32) o[t] = 0.f;
+    if (nq_dev && qi >= *nq_dev) {               // capacity padding row
+        if (qi < pad_band_end(*nq_dev)) {
+            float* o = wf + (size_t)qi * (KP * CIN);
+            for (int t = lane; t < KP * CIN; t += 32) o[t] = 0.f;
+        }
         return;
     }
 
@@ -229,13 +236,14 @@ k_kpconv_agg_mma(const float* __restrict__ q, const float* __restrict__ s, const
     const int c_base = blockIdx.y * (32 * NH);
     const int g = lane >> 2, t = lane & 3;
     float* out = wf + (size_t)qi * (KP * Cin) + c_base;
-    if (nq_dev && qi >= *nq_dev) {               // capacity padding row: zeros
-        for (int p = g; p < KP; p += 8)
+    if (nq_dev && qi >= *nq_dev) {               // capacity padding row
+        if (qi < pad_band_end(*nq_dev))
+            for (int p = g; p < KP; p += 8)
 #pragma unroll
-            for (int h = 0; h < NH; ++h) {
-                reinterpret_cast<float4*>(out + p * Cin + 32 * h + 8 * t)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                reinterpret_cast<float4*>(out + p * Cin + 32 * h + 8 * t)[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+                for (int h = 0; h < NH; ++h) {
+                    reinterpret_cast<float4*>(out + p * Cin + 32 * h + 8 * t)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    reinterpret_cast<float4*>(out + p * Cin + 32 * h + 8 * t)[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
         return;
     }
     // compact the valid (non-shadow) neighbours; count those whose feature row sums to > 0
@@ -364,8 +372,9 @@ k_kpconv_c1(const float* __restrict__ q, const float* __restrict__ s, const int3
     if (ns_dev) Ns = min(Ns, *ns_dev);
     const int width = FUSE ? Cout : KP;
     float* o = out + (size_t)qi * width;
-    if (nq_dev && qi >= *nq_dev) {               // capacity padding row: zeros
-        for (int t = lane; t < width; t += 32) o[t] = 0.f;
+    if (nq_dev && qi >= *nq_dev) {               // capacity padding row
+        if (qi < pad_band_end(*nq_dev))
+            for (int t = lane; t < width; t += 32) o[t] = 0.f;
         return;
     }
     const float qx = q[3 * qi], qy = q[3 * qi + 1], qz = q[3 * qi + 2];
@@ -439,7 +448,8 @@ k_kpconv_agg_small(const float* __restrict__ q, const float* __restrict__ s, con
     if (ns_dev) Ns = min(Ns, *ns_dev);
     float* out = wf + (size_t)qi * (KP * Cin);
     if (nq_dev && qi >= *nq_dev) {
-        for (int t = lane; t < KP * Cin; t += 32) out[t] = 0.f;
+        if (qi < pad_band_end(*nq_dev))
+            for (int t = lane; t < KP * Cin; t += 32) out[t] = 0.f;
         return;
     }
     int n_valid, n_counted;

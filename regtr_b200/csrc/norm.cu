@@ -98,7 +98,7 @@ k_in_finalize(const int32_t* __restrict__ offs, int n_clouds, int C, float eps, 
     }
 }
 
-// out = act((x - mean) * rstd + res), float4 per thread; rows beyond offs[n_clouds] are zeroed.
+// out = act((x - mean) * rstd + res), float4 per thread; rows beyond offs[n_clouds] are padding (see below).
 // FLAGS: additionally emit flags[r] = (sum_c out[r,c] > 0), the "neighbour counts" predicate of the KPConv
 // that consumes `out` (kpconv_blocks.py:409-412), summed in fp64 across the C/4 <= 32 lanes of the row.
 template <bool FLAGS>
@@ -111,7 +111,8 @@ __global__ void k_in_apply(const float* x, const int32_t* __restrict__ offs, int
     if (!FLAGS && !in_range) return;
     const int r = in_range ? (int)(t / c4n) : 0, c = in_range ? (int)(t % c4n) * 4 : 0;
     const size_t o = (size_t)r * C + c;
-    const bool live = in_range && r < offs[n_clouds];          // rows beyond the real count are capacity padding
+    const int n_real = offs[n_clouds];
+    const bool live = in_range && r < n_real;                  // rows beyond the real count are capacity padding
     float y[4] = {0.f, 0.f, 0.f, 0.f};
     if (live) {
         const int cloud = regtr_cloud_of(offs, n_clouds, r);
@@ -129,7 +130,9 @@ __global__ void k_in_apply(const float* x, const int32_t* __restrict__ offs, int
             for (int j = 0; j < 4; ++j) y[j] = y[j] > 0.f ? y[j] : y[j] * slope;
         }
     }
-    if (in_range) *reinterpret_cast<float4*>(out + o) = make_float4(y[0], y[1], y[2], y[3]);   // zeros on padding
+    // padding rows: zeros inside the 128-row tile that straddles the real count (the only padding a consumer
+    // -- a tiled GEMM -- can touch), untouched beyond
+    if (in_range && r < ((n_real + 127) & ~127)) *reinterpret_cast<float4*>(out + o) = make_float4(y[0], y[1], y[2], y[3]);
     if (FLAGS) {                                               // single convergent shuffle site for the whole warp
         double acc = ((double)y[0] + (double)y[1]) + ((double)y[2] + (double)y[3]);
         for (int d = 1; d < c4n; d <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
