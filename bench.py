@@ -57,7 +57,7 @@ def parse():
     ap.add_argument('--checks', type=int, default=1, help='report pose error vs the oracle on one pair')
     ap.add_argument('--attention', default='fp32', choices=['fp32', 'bf16_tc'],
                     help="fp32: parity kernel (default, pose within 1e-4); bf16_tc: tcgen05 tensor-core core")
-    ap.add_argument('--inflight', type=int, default=6,
+    ap.add_argument('--inflight', type=int, default=10,
                     help='independent pairs in flight per GPU (CUDA-graph executors on private streams); 1 = serial')
     ap.add_argument('--graph', type=int, default=1, help='1: CUDA-graph executor (GraphedRegTR); 0: eager forward')
     return ap.parse_args()

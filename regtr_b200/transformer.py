@@ -150,7 +150,8 @@ class TransformerCrossEncoderLayer(nn.Module):
         ks, kl = (plan.xk_start, plan.xk_len) if cross else (plan.q_start, plan.q_len)
         if self.attention_impl == 'bf16_tc' and val_has_pos:
             # fast mode: in-projection with a bf16 epilogue + tcgen05 attention core (TMA-fed, TMEM accumulators)
-            return ops.mha_bf16_tc(x2p, W, b, plan.q_start, plan.q_len, ks, kl, plan.max_len, self.nhead)
+            return ops.mha_bf16_tc(x2p, W, b, plan.q_start, plan.q_len, ks, kl, plan.max_len, self.nhead,
+                                   m_dev=plan.n_dev)
         nd = plan.n_dev
         if val_has_pos:
             qkv = ops.linear(x2p, W, b, m_dev=nd)         # one packed in-projection GEMM
