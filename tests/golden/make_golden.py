@@ -23,6 +23,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 from oracle import ref_bridge  # noqa: E402
 from regtr_b200.config import get_config  # noqa: E402
@@ -172,9 +173,64 @@ def op_fixtures():
     print('ops', len(fx), 'arrays')
 
 
+def eval_fixtures():
+    """Registration metrics: the reference's own est.log writer, 3DMatch benchmark, ModelNet
+    metrics and metric aggregation on seeded synthetic trajectories (tests/golden/eval_inputs.py)."""
+    import tempfile
+    import types
+    from scipy.spatial.transform import Rotation
+    import eval_inputs as ei
+    # environment shims only: numpy aliases removed after the reference's pinned numpy, and nibabel's
+    # mat2quat (absent here) restated with scipy -- the benchmark only uses q's vector part in a quadratic form
+    np.float, np.int = float, int
+    m = ref_bridge.modules()
+    import nibabel.quaternions as nq
+    nq.mat2quat = lambda M: Rotation.from_matrix(np.asarray(M)).as_quat()[[3, 0, 1, 2]]
+    with ref_bridge._in_ref_dir():
+        import benchmark.benchmark_predator as bp
+        import benchmark.benchmark_modelnet as bm
+        import models.generic_reg_model as grm
+    bp.nq = nq
+    fx = {}
+    scenes = ei.make_scenes()
+    with tempfile.TemporaryDirectory() as tmp:
+        gt_dir, log_dir = os.path.join(tmp, 'gt'), os.path.join(tmp, 'log')
+        ei.write_gt(scenes, gt_dir)
+        fake = types.SimpleNamespace(_log_path=log_dir, cfg=types.SimpleNamespace(benchmark='3DMatch'))
+        for scene, d in scenes.items():
+            for src, tgt, T in d['est']:                                  # the reference's own writer, one pair per call
+                batch = {'src_xyz': [None], 'src_path': [f'x/{scene}/cloud_bin_{src}.pth'],
+                         'tgt_path': [f'x/{scene}/cloud_bin_{tgt}.pth']}
+                grm.GenericRegModel._save_3DMatch_log(fake, batch, {'pose': torch.from_numpy(T[None, None, :3].copy())})
+        est_dir = os.path.join(log_dir, '3DMatch')
+        s, recall = bp.benchmark(est_dir, gt_dir)
+        fx['bench_str'] = np.frombuffer(s.encode('utf-8'), dtype=np.uint8)
+        fx['bench_recall'] = np.array(recall)
+        for scene in scenes:
+            fx[f'flags_{scene}'] = np.load(os.path.join(est_dir, scene, 'flag.npy'))
+            fx[f'errors_{scene}'] = np.load(os.path.join(est_dir, scene, 'errors.npy'))
+        fx['est_log_scene_a'] = np.frombuffer(open(os.path.join(est_dir, 'scene-a', 'est.log'), 'rb').read(), dtype=np.uint8)
+    data, pred = ei.modelnet_batch()
+    met = bm.compute_metrics(data, pred)
+    for k, v in met.items():
+        fx[f'mn_{k}'] = np.asarray(v)
+    for k, v in bm.summarize_metrics(met).items():
+        fx[f'mns_{k}'] = np.asarray(v)
+    fake = types.SimpleNamespace(reg_success_thresh_rot=10, reg_success_thresh_trans=0.1,
+                                 logger=types.SimpleNamespace(info=lambda *a, **k: None))
+    per = [grm.GenericRegModel._compute_metrics(fake, {'pose': p}, {'pose': g}) for p, g in ei.pose_batches()]
+    agg = grm.GenericRegModel._aggregate_metrics(fake, per)
+    for k, v in agg.items():
+        fx[f'agg_{k}'] = _np(v)
+    np.savez_compressed(os.path.join(OUT, 'eval.npz'), **fx)
+    print('eval', len(fx), 'arrays; recall', recall)
+    print(s)
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     np.random.seed(0)
+    eval_fixtures()
     op_fixtures()
     for case in FORWARD_CASES:
         forward_fixture(case)
