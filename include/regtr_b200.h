@@ -122,11 +122,15 @@ int regtr_max_pool(const float* x, const int32_t* idx, int Nq, int Ns, const int
  * slope < 0 disables the activation.  In-place (out == x) is allowed.  Rows in [offs[n_clouds], n_cap)
  * are padding: zeroed up to the next multiple of 128, untouched beyond.
  * rowflag_out (optional, n_cap bytes, C/4 a power of two <= 32): flags[r] = (sum_c out[r,c] > 0),
- * the neighbour-count predicate of the KPConv that consumes `out`. */
+ * the neighbour-count predicate of the KPConv that consumes `out`.
+ * counters (optional): regtr_instnorm_counter_bytes(n_clouds, C) bytes of int32, ZERO before the first call
+ * and owned by this op between calls (every call leaves them zero); with them the statistics are
+ * finalised by the last statistics block (one launch fewer), without them by a separate kernel. */
 size_t regtr_instnorm_ws_bytes(int n_cap, int n_clouds, int C);
+size_t regtr_instnorm_counter_bytes(int n_clouds, int C);
 int regtr_instnorm_act(const float* x, const int32_t* offs, int n_clouds, int n_cap, int C, float eps,
                        const float* res, float slope, float* out, uint8_t* rowflag_out,
-                       void* ws, size_t ws_bytes, void* stream);
+                       void* ws, size_t ws_bytes, int32_t* counters, void* stream);
 
 /* ---- dense layers ---------------------------------------------------------------- */
 

@@ -13,7 +13,7 @@ constexpr int IN_CT = 128;    // channels per block
 
 // chunk id -> (cloud, first row, last row) ; chunks never straddle clouds.
 __device__ __forceinline__ bool chunk_of(const int32_t* __restrict__ offs, int n_clouds, int chunk, int& cloud,
-                                         int& r0, int& r1) {
+                                         int& r0, int& r1, int& first, int& count) {
     int acc = 0;
     for (int c = 0; c < n_clouds; ++c) {
         const int a = offs[c], b = offs[c + 1];
@@ -22,6 +22,8 @@ __device__ __forceinline__ bool chunk_of(const int32_t* __restrict__ offs, int n
             cloud = c;
             r0 = a + (chunk - acc) * IN_CH;
             r1 = min(r0 + IN_CH, b);
+            first = acc;                         // the cloud's chunks are [first, first + count)
+            count = nc;
             return true;
         }
         acc += nc;
@@ -30,12 +32,17 @@ __device__ __forceinline__ bool chunk_of(const int32_t* __restrict__ offs, int n
 }
 
 // partial[chunk][c] = (sum, sum of squares) in fp64 over the chunk's rows.  C % 4 == 0.
+// With `counters` (one int per (cloud, channel tile), zero on entry and left zero): the LAST block of a
+// (cloud, channel tile) to finish also reduces that group's partials to stats[cloud][c] = (mean, rstd) --
+// same fixed summation order as k_in_finalize, so the result does not depend on which block that is --
+// and the separate finalize launch disappears.
 __global__ void __launch_bounds__(32 * IN_TY)
 k_in_stats(const float* __restrict__ x, const int32_t* __restrict__ offs, int n_clouds, int C,
-           double2* __restrict__ partial) {
+           double2* __restrict__ partial, int32_t* __restrict__ counters, float eps, float2* __restrict__ stats) {
     __shared__ double red[IN_TY][32][8];
-    int cloud, r0, r1;
-    if (!chunk_of(offs, n_clouds, blockIdx.x, cloud, r0, r1)) return;
+    __shared__ int s_last;
+    int cloud, r0, r1, first, count;
+    if (!chunk_of(offs, n_clouds, blockIdx.x, cloud, r0, r1, first, count)) return;
     const int c = blockIdx.y * IN_CT + threadIdx.x * 4;
     double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
     if (c < C) {
@@ -64,6 +71,43 @@ k_in_stats(const float* __restrict__ x, const int32_t* __restrict__ offs, int n_
             for (int j = 0; j < 4; ++j) { s[j] += red[t][threadIdx.x][j]; ss[j] += red[t][threadIdx.x][4 + j]; }
 #pragma unroll
         for (int j = 0; j < 4; ++j) partial[(size_t)blockIdx.x * C + c + j] = make_double2(s[j], ss[j]);
+    }
+    if (!counters) return;
+    __threadfence();                              // this block's partials are visible before it is counted
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        int32_t* cnt = counters + cloud * gridDim.y + blockIdx.y;
+        s_last = atomicAdd(cnt, 1) == count - 1;
+        if (s_last) *cnt = 0;                     // nobody else touches it any more: restored for the next call
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double fs[4] = {0, 0, 0, 0}, fss[4] = {0, 0, 0, 0};
+    if (c < C) {
+        for (int t = threadIdx.y; t < count; t += IN_TY)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {         // L2 reads: the partials come from other SMs
+                const double2 p = __ldcg(partial + (size_t)(first + t) * C + c + j);
+                fs[j] += p.x; fss[j] += p.y;
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[threadIdx.y][threadIdx.x][j] = fs[j]; red[threadIdx.y][threadIdx.x][4 + j] = fss[j]; }
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        for (int t = 1; t < IN_TY; ++t)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { fs[j] += red[t][threadIdx.x][j]; fss[j] += red[t][threadIdx.x][4 + j]; }
+        const int n = offs[cloud + 1] - offs[cloud];
+        const double dn = n > 0 ? (double)n : 1.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double mean = fs[j] / dn;
+            double var = fss[j] / dn - mean * mean;          // biased variance (InstanceNorm)
+            var = var > 0.0 ? var : 0.0;
+            stats[(size_t)cloud * C + c + j] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+        }
     }
 }
 
@@ -195,9 +239,13 @@ size_t regtr_instnorm_ws_bytes(int n_cap, int n_clouds, int C) {
     return regtr_align((size_t)in_chunks(n_cap, (int)nc) * c * sizeof(double2)) + regtr_align(nc * c * sizeof(float2));
 }
 
+size_t regtr_instnorm_counter_bytes(int n_clouds, int C) {
+    return sizeof(int32_t) * (size_t)(n_clouds > 0 ? n_clouds : 1) * (size_t)regtr_cdiv(C > 0 ? C : 1, IN_CT);
+}
+
 int regtr_instnorm_act(const float* x, const int32_t* offs, int n_clouds, int n_cap, int C, float eps,
                        const float* res, float slope, float* out, uint8_t* rowflag_out, void* ws, size_t ws_bytes,
-                       void* stream_) {
+                       int32_t* counters, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (!offs || n_clouds <= 0 || n_cap < 0 || C <= 0) return REGTR_ERR_ARG;
     if (C % 4 != 0) return REGTR_ERR_UNSUPPORTED;
@@ -208,10 +256,12 @@ int regtr_instnorm_act(const float* x, const int32_t* offs, int n_clouds, int n_
     double2* partial = (double2*)ws;
     float2* stats = (float2*)((char*)ws + regtr_align((size_t)chunks * C * sizeof(double2)));
     dim3 block(32, IN_TY);
-    k_in_stats<<<dim3(chunks, regtr_cdiv(C, IN_CT)), block, 0, st>>>(x, offs, n_clouds, C, partial);
+    k_in_stats<<<dim3(chunks, regtr_cdiv(C, IN_CT)), block, 0, st>>>(x, offs, n_clouds, C, partial, counters, eps, stats);
     REGTR_CHECK_LAUNCH();
-    k_in_finalize<<<dim3(n_clouds, regtr_cdiv(C, 32)), block, 0, st>>>(offs, n_clouds, C, eps, partial, stats);
-    REGTR_CHECK_LAUNCH();
+    if (!counters) {                              // no persistent counters: separate finalize launch
+        k_in_finalize<<<dim3(n_clouds, regtr_cdiv(C, 32)), block, 0, st>>>(offs, n_clouds, C, eps, partial, stats);
+        REGTR_CHECK_LAUNCH();
+    }
     if (rowflag_out) {
         const int c4n = C / 4;
         if (c4n > 32 || (c4n & (c4n - 1))) return REGTR_ERR_UNSUPPORTED;   // the row must sit inside one warp

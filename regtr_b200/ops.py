@@ -57,12 +57,14 @@ def _chk(t, dtype, name, dims=None):
 WS_NAMESPACE = None
 
 
-def workspace(nbytes: int, device, slot: str = 'default') -> torch.Tensor:
-    """Per-(device, namespace, slot) grow-only scratch buffer (stream-ordered reuse)."""
+def workspace(nbytes: int, device, slot: str = 'default', zero: bool = False) -> torch.Tensor:
+    """Per-(device, namespace, slot) grow-only scratch buffer (stream-ordered reuse).
+    zero=True: allocated zero-filled (state that an op keeps zero between its own calls)."""
     key = (device.index if device.index is not None else torch.cuda.current_device(), WS_NAMESPACE, slot)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, device=device)
+        n = max(int(nbytes * 1.25), 4096 if zero else 1 << 20)
+        buf = (torch.zeros if zero else torch.empty)(n, dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
 
@@ -237,9 +239,11 @@ def instnorm_act(x, offs, n_clouds: int, res=None, slope: float = -1.0, eps: flo
     flags = None
     if want_flags and C // 4 <= 32 and (C // 4) & (C // 4 - 1) == 0 and 'norm' not in _ABLATE:
         flags = torch.empty(max(n, 1), dtype=torch.uint8, device=x.device)
+    # self-resetting completion counters: the last statistics block of a (cloud, channel tile) finalises it
+    cnt = workspace(L.regtr_instnorm_counter_bytes(n_clouds, C), x.device, 'instnorm_cnt', zero=True)
     _lib.check(L.regtr_instnorm_act(_p(x), _p(offs), n_clouds, n, C, float(eps), _p(res), float(slope), _p(out),
-                                    _p(flags), _p(ws), ws.numel(), _stream()), 'regtr_instnorm_act')
-    _count(3)
+                                    _p(flags), _p(ws), ws.numel(), _p(cnt), _stream()), 'regtr_instnorm_act')
+    _count(2)
     return (out, flags) if want_flags else out
 
 
