@@ -102,3 +102,33 @@ def test_pair_stream_order_and_errors(tmp_path):
     os.remove(tmp_path / 'test' / 'scene' / 'cloud_bin_5.pth')
     with pytest.raises(Exception):
         list(D.PairStream(ds, batches, workers=2, depth=2))
+
+
+def test_sequence_helpers_match_reference():
+    """regtr_b200.seq vs utils/seq_manipulation.py (imported when the reference is present), plus a padded
+    round trip."""
+    from regtr_b200 import seq as S
+    rng = np.random.default_rng(2)
+    seqs = [torch.from_numpy(rng.normal(size=(n, 5)).astype(np.float32)) for n in (7, 3, 11, 1)]
+    padded, mask, lens = S.pad_sequence(seqs, require_padding_mask=True, require_lens=True)
+    assert padded.shape == (11, 4, 5) and mask.shape == (4, 11) and lens == [7, 3, 11, 1]
+    assert mask[1, 3:].all() and not mask[1, :3].any() and not mask[2].any()
+    back = S.unpad_sequences(padded, lens)
+    assert all(torch.equal(a, b) for a, b in zip(back, seqs))
+    stacked = torch.cat(seqs)
+    src, tgt = S.split_src_tgt(stacked, torch.tensor(lens))
+    assert len(src) == 2 and torch.equal(tgt[1], seqs[3])
+    if os.path.isdir(REF):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location('ref_seq', os.path.join(REF, 'src', 'utils', 'seq_manipulation.py'))
+        R = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(R)
+        for kw in (dict(), dict(require_padding_mask=True, require_lens=True)):
+            a, b = S.pad_sequence(seqs, **kw), R.pad_sequence(seqs, **kw)
+            assert torch.equal(a[0], b[0]) and (a[1] is None) == (b[1] is None) and a[2] == b[2]
+            if a[1] is not None:
+                assert torch.equal(a[1], b[1])
+        six = torch.from_numpy(rng.normal(size=(6, 11, 4, 5)).astype(np.float32))
+        assert all(torch.equal(x, y) for x, y in zip(S.unpad_sequences(six, lens), R.unpad_sequences(six, lens)))
+        a, b = S.split_src_tgt(stacked, lens), R.split_src_tgt(stacked, lens)
+        assert all(torch.equal(x, y) for x, y in zip(a[0] + a[1], b[0] + b[1]))
