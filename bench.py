@@ -443,7 +443,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and args.cpu_baseline:
         log('cpu baseline ...')
-        cpu, _ = time_cpu(cfg, sd, pool, n_pairs=3)
+        cpu, _ = time_cpu(cfg, sd, pool, n_pairs=10)        # ~10 s of CPU work on the box's cores
         log(f'cpu baseline {cpu["value"]:.3f} pairs/s on {cpu["cores"]} threads')
 
     # ---------------- pose error vs the oracle on one pair (reported, also covered by tests/)
