@@ -162,6 +162,14 @@ class RegTR(nn.Module):
             'pose': core['pose'],
         }
 
+    def compute_loss(self, pred, batch):
+        """Loss VALUES of a forward (regtr.py:237-294: overlap BCE, InfoNCE feature losses, L1 correspondence
+        loss, weighted total) as `test_step` reports them; forward-only -- gradients do not flow into the CUDA
+        kernels yet.  Needs batch['pose'], ['src_overlap'], ['tgt_overlap'], ['kpconv_meta']."""
+        from . import losses
+        with torch.no_grad():
+            return losses.compute_loss(self, pred, batch)
+
     @torch.no_grad()
     def forward(self, batch):
         """Eager path: exact shapes, one host sync (pyramid sizes) before the encoder."""

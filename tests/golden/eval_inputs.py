@@ -86,3 +86,24 @@ def pose_batches(seed=9, n_batches=3, L=6, B=4):
                          for l in range(L)])
         out.append((torch.from_numpy(pred.astype(np.float32)), torch.from_numpy(gt.astype(np.float32))))
     return out
+
+
+def loss_state_dict(sd, seed=31):
+    """The benchmark state_dicts initialise the InfoNCE matrices to identity; use a seeded dense W so that the
+    symmetrisation (triu + triu^T) matters."""
+    import torch
+    rng = np.random.default_rng(seed)
+    sd = dict(sd)
+    for k in ('feature_criterion.W', 'feature_criterion_un.W'):
+        sd[k] = torch.from_numpy((rng.normal(size=tuple(sd[k].shape)) * 0.1).astype(np.float32))
+    return sd
+
+
+def loss_inputs(pairs, src_lens, tgt_lens, seed=33):
+    """Ground-truth pose (3,4) per pair from the generator + seeded level-0 overlap masks."""
+    import torch
+    rng = np.random.default_rng(seed)
+    pose = np.stack([np.asarray(p['pose'], dtype=np.float32)[:3] for p in pairs])
+    return {'pose': torch.from_numpy(pose),
+            'src_overlap': [torch.from_numpy(rng.random(n) < 0.6) for n in src_lens],
+            'tgt_overlap': [torch.from_numpy(rng.random(n) < 0.5) for n in tgt_lens]}

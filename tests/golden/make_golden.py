@@ -227,10 +227,33 @@ def eval_fixtures():
     print(s)
 
 
+def loss_fixture():
+    """RegTR.compute_loss of the unmodified reference on the `fwd_modelnet_b1` forward with seeded overlap
+    masks and ground-truth pose (tests/golden/eval_inputs.py:loss_inputs)."""
+    import eval_inputs as ei
+    cfg_name, wseed, makers = FORWARD_CASES['fwd_modelnet_b1'][:3]
+    cfg = get_config(cfg_name)
+    sd = random_state_dict(cfg, wseed)
+    sd = ei.loss_state_dict(sd)
+    model = ref_bridge.build_reference_model(cfg, sd)
+    pairs = [mk() for mk in makers]
+    batch = {'src_xyz': [torch.from_numpy(p['src_xyz']) for p in pairs], 'tgt_xyz': [torch.from_numpy(p['tgt_xyz']) for p in pairs]}
+    with torch.no_grad():
+        pred = model(batch)
+        batch.update(ei.loss_inputs(pairs, [int(x.shape[0]) for x in batch['src_xyz']], [int(x.shape[0]) for x in batch['tgt_xyz']]))
+        losses = model.compute_loss(pred, batch)
+    fx = {f'loss_{k}': _np(v) for k, v in losses.items()}
+    for lvl in range(len(batch['kpconv_meta']['points'])):
+        fx[f'overlap_pyr_{lvl}'] = _np(batch['overlap_pyr'][f'pyr_{lvl}'])
+    np.savez_compressed(os.path.join(OUT, 'loss.npz'), **fx)
+    print('loss', {k: float(v) for k, v in fx.items() if k.startswith('loss_')})
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     np.random.seed(0)
     eval_fixtures()
+    loss_fixture()
     op_fixtures()
     for case in FORWARD_CASES:
         forward_fixture(case)
