@@ -7,8 +7,9 @@ Host-side mirror of the inference branch of
     ndarray per cloud;
   * `collate_pair` (/root/reference/src/data_loaders/collate_functions.py:4-22): variable-size fields stay
     python lists, `pose` is stacked (B,3,4), `overlap_p` becomes a tensor.
-Training-only fields (overlap masks, correspondences: `compute_overlap`, the precomputed h5 file) and the
-augmentation transforms are outside this round's scope.
+The overlap masks / correspondences the losses need are computed on the fly (`compute_overlap`, the branch the
+reference takes when its precomputed h5 file is missing); the training augmentation transforms are outside
+this round's scope.
 
 At >1k pairs/s per GPU the loader is part of the path: `PairStream` reads ahead on worker threads, pins the
 host clouds (so that `GraphedRegTR.submit` can issue asynchronous H2D copies straight into its static
@@ -39,12 +40,32 @@ def collate_pair(list_data: Sequence[Dict]) -> Dict:
     return data
 
 
+def compute_overlap(src: np.ndarray, tgt: np.ndarray, search_radius: float):
+    """Overlap region and mutual correspondences of two ALIGNED clouds (utils/pointcloud.py:8-65): a point is
+    in the overlap if the other cloud has a point within `search_radius`; its correspondence is the nearest such
+    point; `src_tgt_corr` (2, M) keeps the mutual ones (with the reference's `src_corr > 0` quirk: a source
+    point matched to target index 0 is never reported).  The reference searches with Open3D's KDTreeFlann
+    (absent here: parity unpinned for ties and points exactly on the radius); this uses scipy's cKDTree."""
+    from scipy.spatial import cKDTree
+    def nearest_within(a, b):                       # for every point of a: nearest point of b within the radius, or -1
+        d, i = cKDTree(b).query(a, k=1, distance_upper_bound=search_radius)
+        return np.where(np.isfinite(d), i, -1).astype(np.int64)
+    tgt_corr = nearest_within(tgt, src)
+    src_corr = nearest_within(src, tgt)
+    mutual = np.logical_and(tgt_corr[src_corr] == np.arange(len(src_corr)), src_corr > 0)
+    return src_corr >= 0, tgt_corr >= 0, np.stack([np.nonzero(mutual)[0], src_corr[mutual]])
+
+
 class ThreeDMatchPairs(torch.utils.data.Dataset):
     """Inference view of `ThreeDMatchDataset`: item -> {src_xyz, tgt_xyz (N,3) fp32, pose (3,4) fp32 (src -> tgt),
     idx, src_path, tgt_path, overlap_p}.  `root` holds the `test/<scene>/cloud_bin_<i>.pth` files,
     `info_file` is the benchmark's pickle."""
 
-    def __init__(self, root: str, info_file: str, pin: bool = False):
+    def __init__(self, root: str, info_file: str, pin: bool = False, overlap_radius: Optional[float] = None):
+        """overlap_radius (cfg.overlap_radius, 0.0375 for 3DMatch): also produce the training / loss fields
+        `src_overlap`, `tgt_overlap`, `correspondences` like the reference does when the precomputed h5 file is
+        missing (threedmatch.py:79-86)."""
+        self.overlap_radius = overlap_radius
         with open(info_file, 'rb') as fid:
             self.infos = pickle.load(fid)
         for k in ('rot', 'trans', 'src', 'tgt', 'overlap'):
@@ -62,10 +83,17 @@ class ThreeDMatchPairs(torch.utils.data.Dataset):
 
     def __getitem__(self, item):
         pose = np.concatenate([self.infos['rot'][item], self.infos['trans'][item]], axis=-1)   # se3_init
-        return {'src_xyz': self._cloud(self.infos['src'][item]), 'tgt_xyz': self._cloud(self.infos['tgt'][item]),
-                'pose': torch.from_numpy(pose).float(), 'idx': item,
-                'src_path': self.infos['src'][item], 'tgt_path': self.infos['tgt'][item],
-                'overlap_p': self.infos['overlap'][item]}
+        out = {'src_xyz': self._cloud(self.infos['src'][item]), 'tgt_xyz': self._cloud(self.infos['tgt'][item]),
+               'pose': torch.from_numpy(pose).float(), 'idx': item,
+               'src_path': self.infos['src'][item], 'tgt_path': self.infos['tgt'][item],
+               'overlap_p': self.infos['overlap'][item]}
+        if self.overlap_radius is not None:
+            s64 = np.asarray(torch.load(os.path.join(self.root, out['src_path']), weights_only=False))
+            t64 = np.asarray(torch.load(os.path.join(self.root, out['tgt_path']), weights_only=False))
+            sm, tm, corr = compute_overlap(s64 @ pose[:, :3].T + pose[:, 3], t64, self.overlap_radius)
+            out.update(src_overlap=torch.from_numpy(sm), tgt_overlap=torch.from_numpy(tm),
+                       correspondences=torch.from_numpy(corr))
+        return out
 
     def sizes(self, items: Optional[Iterable[int]] = None) -> List[int]:
         """Total points per pair WITHOUT loading the clouds would need an index; this loads each once."""

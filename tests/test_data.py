@@ -132,3 +132,25 @@ def test_sequence_helpers_match_reference():
         assert all(torch.equal(x, y) for x, y in zip(S.unpad_sequences(six, lens), R.unpad_sequences(six, lens)))
         a, b = S.split_src_tgt(stacked, lens), R.split_src_tgt(stacked, lens)
         assert all(torch.equal(x, y) for x, y in zip(a[0] + a[1], b[0] + b[1]))
+
+
+def test_compute_overlap_properties(tmp_path):
+    rng = np.random.default_rng(4)
+    tgt = rng.uniform(0, 1, size=(400, 3))
+    src = np.concatenate([tgt[:250] + rng.normal(scale=0.002, size=(250, 3)), rng.uniform(2, 3, size=(80, 3))])
+    sm, tm, corr = D.compute_overlap(src, tgt, 0.02)
+    assert sm[:250].all() and not sm[250:].any()                 # the shifted copies overlap, the far blob does not
+    assert tm[:250].all() and tm[250:].sum() < 40
+    s_idx, t_idx = corr
+    assert (np.linalg.norm(src[s_idx] - tgt[t_idx], axis=1) < 0.02).all()
+    assert (s_idx[t_idx == s_idx] > 0).all() and len(s_idx) > 200     # mutual matches, index 0 excluded (reference quirk)
+    # brute-force nearest neighbour agrees
+    d = np.linalg.norm(src[:, None] - tgt[None], axis=-1)
+    assert np.array_equal(sm, d.min(1) < 0.02)
+    ds, infos = _make_dataset(tmp_path)
+    ds.overlap_radius = 0.5
+    it = ds[2]
+    assert it['src_overlap'].dtype == torch.bool and it['src_overlap'].shape[0] == it['src_xyz'].shape[0]
+    assert it['correspondences'].shape[0] == 2
+    b = D.collate_pair([ds[0], ds[1]])
+    assert isinstance(b['correspondences'], list) and len(b['src_overlap']) == 2
