@@ -179,17 +179,6 @@ def kpconv_algorithmic_bytes(info):
     return Nq * K * 4 + nnz * (12 + Cin * 4) + Nq * 12 + Nq * Cout * 4 + 15 * Cin * Cout * 4
 
 
-def peaks():
-    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
-    if os.path.exists(path):
-        try:
-            d = json.load(open(path))
-            return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
-        except Exception:
-            pass
-    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
-
-
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path on the host cores."""
     if rank != 0:
@@ -228,6 +217,177 @@ def run_reference(args, rank, world):
                 e2e=dict(value=v, unit='pairs/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line), flush=True)
+
+
+def peak_table():
+    """Roofline denominators: measured (MEASURED_PEAKS.json, driver-written) or the profiling guide's fallback."""
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        d = json.load(open(path))
+        return dict(hbm_gbs=float(d['hbm_gbs']), bf16_tflops=float(d['bf16_tflops']),
+                    bf16_tflops_sustained=float(d.get('bf16_tflops_sustained', d['bf16_tflops'])),
+                    source='measured (MEASURED_PEAKS.json)')
+    except Exception:
+        return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0,
+                    source='fallback (B200_PROFILING.md: 6.65 TB/s, 1.59 PFLOP/s)')
+
+
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel family, read at run time from the
+    committed ncu summary (profiles/r02_ncu_traffic.json, written by scripts/ncu_summary.py from one
+    `ncu --set full` capture of this workload); None when no capture of this build is committed."""
+    try:
+        d = json.load(open(os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')))
+        return d.get(kernel_key)
+    except Exception:
+        return None
+
+
+def measure_stages(model, batch_at, resident, flush, W, B, reps=20):
+    """Per-stage GPU time at the reference's `_TIMEIT` boundaries (regtr.py:108-216: preprocess | encoder |
+    attention + decoder | pose) from CUDA events between four back-to-back graph replays of ONE serial forward
+    (GraphedRegTR(stages=True)), L2 flushed before each forward, plus the single-stream latency of the
+    one-graph executor.  Median over `reps` forwards."""
+    from regtr_b200.regtr import GraphedRegTR
+    staged, single = GraphedRegTR(model, stages=True), GraphedRegTR(model)
+    per = {nm: [] for nm in GraphedRegTR.STAGES}
+    lat = []
+    for i in range(3):
+        staged(batch_at(W + i, resident)[0]); single(batch_at(W + i, resident)[0])
+    for i in range(reps):
+        batch = batch_at(W + i, resident)[0]
+        flush.zero_()
+        ticket = staged.submit(batch)
+        staged.result(ticket)
+        for nm, v in staged.stage_ms(ticket[0]).items():
+            per[nm].append(v)
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        single.result(single.submit(batch))
+        e1.record()
+        torch.cuda.synchronize()
+        lat.append(e0.elapsed_time(e1))
+    med = {nm: statistics.median(v) for nm, v in per.items()}
+    return dict(stage_ms=med, stage_sum_ms=sum(med.values()), single_stream_latency_ms=statistics.median(lat),
+                pairs_per_forward=B, note='serial forward (nothing else on the GPU), L2 flushed before each; '
+                'four stage graphs replayed back to back with CUDA events between them; latency = one-graph '
+                'executor incl. input copy and result D2H')
+
+
+def retime(fn, flush, reps=3):
+    """[L2 flush][event][launch][event], best of `reps`, and the same launch again with its inputs L2-resident."""
+    best = best_w = None
+    for _ in range(reps):
+        flush.zero_()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record(); fn(); ev[1].record()
+        ev[2].record(); fn(); ev[3].record()
+        torch.cuda.synchronize()
+        t, tw = ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3])
+        best = t if best is None else min(best, t)
+        best_w = tw if best_w is None else min(best_w, tw)
+    return best, best_w
+
+
+def measure_rooflines(model, batch_at, resident, flush, W, K, B, ms_per_step):
+    """Roofline entries of the three north-star kernel families and of the whole forward, from the REAL shapes of
+    one traced eager forward: every launch is re-timed alone on the launching stream right after an L2 flush."""
+    from regtr_b200 import ops
+    pk = peak_table()
+    tf32_peak = pk['bf16_tflops'] / 2.0                    # dense TF32 = half the measured bf16 rate (burst: kernels timed alone)
+    ops.KPCONV_TRACE, ops.TRACE = [], []
+    flush.zero_()
+    model(batch_at(W, resident)[0])
+    torch.cuda.synchronize()
+    ktr, tr = ops.KPCONV_TRACE, ops.TRACE
+    ops.KPCONV_TRACE = ops.TRACE = None
+
+    # ---- KPConv neighbour gather (HBM bound, SURVEY 8d algorithmic bytes)
+    gather_ms = warm_ms = 0.0
+    per_launch = []
+    agg_flops = 0.0
+    for _, _, info in ktr:
+        t, tw = retime(lambda: ops.kpconv_aggregate(*info['args'], row_flags=info.get('row_flags')), flush)
+        gather_ms += t; warm_ms += tw
+        nnz = int((info['idx'] < info['Ns']).sum().item())
+        agg_flops += nnz * 15 * 12 + 2.0 * info['Nq'] * 15 * info['K'] * info['Cin']
+        per_launch.append(dict(Nq=info['Nq'], Cin=info['Cin'], us=round(t * 1e3, 1), us_l2_warm=round(tw * 1e3, 1)))
+    step_bytes = sum(kpconv_algorithmic_bytes(info) for _, _, info in ktr)
+    ach = step_bytes / (gather_ms * 1e-3) / 1e9
+    gather = dict(name='kpconv_gather', bound='hbm',
+                  kernel='KPConv neighbour gather + kernel-point influence + aggregation (one launch per KPConv, each '
+                         'timed alone right after an L2 flush); bytes = SURVEY 8d algorithmic bytes of the KPConv op',
+                  achieved=ach, peak=pk['hbm_gbs'], unit='GB/s', frac=ach / pk['hbm_gbs'],
+                  traffic=ncu_traffic('kpconv_gather'), traffic_unit='bytes/launch (committed ncu capture)',
+                  peak_source=pk['source'], launches=len(ktr), algorithmic_bytes_per_step=step_bytes,
+                  algorithmic_bytes_per_launch=step_bytes / max(len(ktr), 1), ms_per_step=gather_ms,
+                  ms_per_step_l2_warm=warm_ms, frac_l2_warm=step_bytes / (warm_ms * 1e-3) / 1e9 / pk['hbm_gbs'],
+                  per_launch=per_launch)
+
+    # ---- dense layers: 3xTF32 tcgen05 GEMM (tensor bound); MMA flops = 2*M*N*K*3
+    g_ms = g_flops = 0.0
+    shapes = {}
+    for kind, info, fn in tr:
+        if kind != 'gemm':
+            continue
+        t, _ = retime(fn, flush)
+        fl = 2.0 * info['M'] * info['N'] * info['K']
+        g_ms += t; g_flops += fl
+        key = (info['M'], info['N'], info['K'])
+        c = shapes.setdefault(key, [0, 0.0])
+        c[0] += 1; c[1] += t
+    n_gemm = sum(c[0] for c in shapes.values())
+    ach = 3.0 * g_flops / (g_ms * 1e-3) / 1e12
+    top = sorted(shapes.items(), key=lambda kv: -kv[1][1])[:12]
+    gemm = dict(name='gemm_tf32x3', bound='tensor',
+                kernel='k_gemm_tf32x3 (+ split-K reduce): every nn.Linear and the KPConv weight contraction; flops = '
+                       '2*M*N*K*3 TF32 MMA flops (3xTF32 split) summed over the launches of one forward, each timed alone '
+                       'after an L2 flush',
+                achieved=ach, peak=tf32_peak, unit='TFLOP/s', frac=ach / tf32_peak, traffic=ncu_traffic('gemm_tf32x3'),
+                peak_source=pk['source'] + ': bf16_tflops / 2 (dense TF32)', launches=n_gemm, ms_per_step=g_ms,
+                fp32_equiv_flops_per_step=g_flops, fp32_equiv_tflops=g_flops / (g_ms * 1e-3) / 1e12,
+                top_shapes=[dict(M=k[0], N=k[1], K=k[2], launches=c[0], us=round(c[1] * 1e3, 1),
+                                 tf32_tflops=round(3 * 2.0 * k[0] * k[1] * k[2] * c[0] / (c[1] * 1e-3) / 1e12, 1))
+                            for k, c in top])
+
+    # ---- attention core (QK^T and PV): 4*q*k*E flops per problem, x3 for the 3xTF32 split
+    a_ms = a_flops = 0.0
+    n_att = 0
+    for kind, info, fn in tr:
+        if kind != 'mha':
+            continue
+        t, _ = retime(fn, flush)
+        a_ms += t; a_flops += 4.0 * info['pairs_qk'] * info['E']; n_att += 1
+    att = None
+    if n_att:
+        ach = 3.0 * a_flops / (a_ms * 1e-3) / 1e12
+        att = dict(name='attention_core', bound='tensor',
+                   kernel='attention core (softmax(QK^T)V per head, varlen problems): 4*q*k*E flops per problem, x3 '
+                          '(3xTF32 split), self and cross launches of the 6 layers',
+                   achieved=ach, peak=tf32_peak, unit='TFLOP/s', frac=ach / tf32_peak, traffic=ncu_traffic('attention_core'),
+                   peak_source=pk['source'] + ': bf16_tflops / 2 (dense TF32)', launches=n_att, ms_per_step=a_ms,
+                   fp32_equiv_flops_per_step=a_flops)
+
+    # ---- whole forward: algorithmic fp32-equivalent flops and bytes of one step / the pipelined ms_per_step
+    total_flops = g_flops + a_flops + agg_flops
+    sus = pk['bf16_tflops_sustained'] / 2.0
+    tf = total_flops / (ms_per_step * 1e-3) / 1e12
+    whole = dict(name='whole_forward', bound='tensor',
+                 kernel='whole forward at the benchmarked throughput: fp32-equivalent algorithmic flops of one step '
+                        '(dense layers + attention core + KPConv aggregation/influence) / ms_per_step; the fp32-accurate '
+                        'path issues 3 TF32 MMA flops per algorithmic flop',
+                 achieved=3.0 * tf, peak=sus, unit='TFLOP/s', frac=3.0 * tf / sus, traffic=None,
+                 peak_source=pk['source'] + ': bf16_tflops_sustained / 2 (dense TF32, kernel inside a long step)',
+                 fp32_equiv_flops_per_step=total_flops, fp32_equiv_tflops=tf,
+                 hbm_algorithmic_bytes_per_step=step_bytes,
+                 hbm_frac_on_gather_bytes=step_bytes / (ms_per_step * 1e-3) / 1e9 / pk['hbm_gbs'],
+                 ms_per_step=ms_per_step, pairs_per_step=B,
+                 kernel_ms_alone=dict(gather=gather_ms, gemm=g_ms, attention_core=a_ms),
+                 kpconv_op_ms_per_step_eager=sum(a.elapsed_time(b) for a, b, _ in ktr))
+    rooflines = [r for r in (gather, gemm, att, whole) if r is not None]
+    dominant = max((r for r in rooflines if r['name'] != 'whole_forward'), key=lambda r: r['ms_per_step'])
+    return dominant, rooflines
 
 
 def main():
@@ -295,7 +455,7 @@ def main():
         out = runner(batch)                     # graph executor: packs the host clouds, one H2D copy
         if world > 1:
             return gather_poses(out['pose'], B * world).cpu(), ids
-        return (out['pose_host'] if 'pose_host' in out else out['pose'].cpu()), ids
+        return (out['host_pose'] if 'host_pose' in out else out['pose'].cpu()), ids
 
     sampler = ClockSampler(local) if rank == 0 else None     # started early: nvidia-smi needs ~0.1 s to report
     log(f'pool ready ({n_pool} pairs, {sum(len(a) + len(b) for a, b in pool) // n_pool} pts/pair); warm-up')
@@ -318,10 +478,10 @@ def main():
         for i in range(K):
             done = pipe.submit(batch_at(W + i, src)[0], pre_hook=flush.zero_)
             if done is not None:
-                outs.append(done['pose_host'].clone())
+                outs.append(done['host_pose'].clone())
         t_cpu = time.perf_counter() - t_cpu
         log(f'host time in submit/result: {1e3 * t_cpu / K:.3f} ms/step')
-        outs += [o['pose_host'].clone() for o in pipe.drain()]
+        outs += [o['host_pose'].clone() for o in pipe.drain()]
         pipe.join()
         if world > 1:                           # the run's poses, gathered over the ranks (288 B / pair)
             gather_poses(torch.cat(outs, dim=1).to(dev, non_blocking=True), B * K * world)
@@ -373,7 +533,7 @@ def main():
         run_pipelined(host)
         barrier()
         t_e2e_ms, outs = run_pipelined(host)
-        d2h = outs[-1].numel() * 4
+        d2h = next(iter(pipe.slots[0].graphs.values()))['tail_host'].numel() * 4    # level sizes + status + pose, one copy
         barrier()
     clocks = sampler.stop() if sampler else None
     log(f'e2e: {t_e2e_ms / K:.3f} ms/step; clocks {clocks}')
@@ -384,60 +544,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_dev_ms, t_e2e_ms = t.tolist()
 
-    # ---------------- roofline of the dominant kernel (KPConv gather + contraction), rank 0
-    roof = None
+    # ---------------- where the time goes: stage times at the reference's _TIMEIT boundaries + rooflines, rank 0
+    roof = rooflines = stage_rec = None
     if rank == 0:
-        ops.KPCONV_TRACE = []
-        nsteps = min(K, 5)
-        for i in range(nsteps):                 # eager forward: the trace hooks live in ops.kpconv
-            flush.zero_()
-            model(batch_at(W + i, resident)[0])
-        torch.cuda.synchronize()
-        tr, ops.KPCONV_TRACE = ops.KPCONV_TRACE, None
-        # Re-time the dominant kernel (k_kpconv_agg: neighbour gather + influence + aggregation) launch
-        # by launch on its own stream: [L2 flush][event][kernel][event], 3 repetitions each, over the
-        # 11 KPConv calls of the last traced step.  The flush (~80 us) hides the launch latency.
-        last = tr[-11:] if len(tr) >= 11 else tr
-        gather_ms = warm_ms = 0.0
-        per_launch = []
-        for _, _, info in last:
-            best = best_w = None
-            for _ in range(3):
-                flush.zero_()
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-                ev[0].record()
-                ops.kpconv_aggregate(*info['args'], row_flags=info.get('row_flags'))      # cold: L2 just flushed
-                ev[1].record()
-                ev[2].record()
-                ops.kpconv_aggregate(*info['args'], row_flags=info.get('row_flags'))      # inputs L2-resident, as
-                ev[3].record()                                                            # behind their producer
-                torch.cuda.synchronize()
-                t, tw = ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3])
-                best = t if best is None else min(best, t)
-                best_w = tw if best_w is None else min(best_w, tw)
-            gather_ms += best
-            warm_ms += best_w
-            per_launch.append(dict(Nq=info['Nq'], Cin=info['Cin'], us=round(best * 1e3, 1),
-                                   us_l2_warm=round(best_w * 1e3, 1)))
-        tot_ms = sum(a.elapsed_time(b) for a, b, _ in tr) / nsteps          # whole KPConv op incl. weight GEMM (eager)
-        step_bytes = sum(kpconv_algorithmic_bytes(info) for _, _, info in last)
-        peak, peak_src = peaks()
-        ach = step_bytes / (gather_ms * 1e-3) / 1e9
-        roof = dict(bound='hbm',
-                    kernel='k_kpconv_agg_mma / k_kpconv_c1 (+k_row_flags where the flags are not fused upstream): KPConv neighbour '
-                           'gather + kernel-point influence + aggregation, 11 launches/pair, each timed alone right after '
-                           'an L2 flush; bytes = SURVEY 8d algorithmic bytes of the KPConv op',
-                    achieved=ach, peak=peak, unit='GB/s', frac=ach / peak,
-                    # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 11 launches of one
-                    # `ncu --set full` capture of this workload (profiles/r01_ncu_kpconv_agg_mma_summary.csv):
-                    # 55.5 MB per pair against 590 MB algorithmic -- the 126 MB L2 absorbs the row reuse
-                    traffic=55.5e6 / 11, traffic_unit='bytes/launch (ncu capture, batch 1)', peak_source=peak_src,
-                    algorithmic_bytes_per_launch=step_bytes / max(len(last), 1),
-                    algorithmic_bytes_per_step=step_bytes, gather_ms_per_step=gather_ms,
-                    # the same launches with their inputs still in L2 (the state behind the producer kernel
-                    # inside a forward); `achieved`/`frac` above are the conservative cold-L2 figures
-                    gather_ms_per_step_l2_warm=warm_ms, frac_l2_warm=step_bytes / (warm_ms * 1e-3) / 1e9 / peak,
-                    kpconv_op_ms_per_step_eager=tot_ms, per_launch=per_launch)
+        stage_rec = measure_stages(model, batch_at, resident, flush, W, B)
+        roof, rooflines = measure_rooflines(model, batch_at, resident, flush, W, K, B, t_dev_ms / K)
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
@@ -475,7 +586,8 @@ def main():
                                      'per-step CUDA events, L2 flush between steps not timed'),
             e2e=dict(value=pairs / (t_e2e_ms * 1e-3), unit='pairs/s', h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h, ms_per_step=t_e2e_ms / K),
-            gpu_launches=launches, clocks=clocks, roofline=roof, cpu_baseline=cpu,
+            gpu_launches=launches, clocks=clocks, roofline=roof, rooflines=rooflines, stages=stage_rec,
+            cpu_baseline=cpu,
             pose_err_vs_oracle=pose_err, impl='b200')
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -35,7 +35,6 @@ extern "C" {
 #define REGTR_ERR_ARG (-1)        /* null pointer / negative size / unsupported shape */
 #define REGTR_ERR_WORKSPACE (-2)  /* workspace too small */
 #define REGTR_ERR_UNSUPPORTED (-3)
-#define REGTR_ERR_CUBLAS (-4)
 
 #define REGTR_STATUS_KEY_RANGE 1u /* a voxel / cell coordinate left the 16-bit key range */
 #define REGTR_STATUS_CAPACITY 2u  /* a capacity-bounded output (sub-sampled level) overflowed; results truncated */
@@ -94,8 +93,11 @@ int regtr_ball_query(const float* q, const int32_t* q_offs, const int32_t* q_ord
  * nq_dev / ns_dev (optional, device int32): actual query / support counts when Nq / Ns are
  * capacities (static-shape pipelines); rows >= *nq_dev are padding (zeroed up to the next multiple of
  * 128, untouched beyond -- consumers work in 128-row tiles); the shadow index is *ns_dev.
- * ws: regtr_kpconv_ws_bytes(Nq, Ns, Cin) bytes (aggregated features + row flags). */
+ * ws: regtr_kpconv_fwd_ws_bytes(Nq, Ns, Cin, Cout) bytes (aggregated features + row flags + the split
+ * transposed weights + the GEMM's workspace; the contraction runs on regtr_gemm_tf32x3 -- no library GEMM).
+ * regtr_kpconv_ws_bytes(Nq, Ns, Cin) is the part regtr_kpconv_aggregate alone needs (wf + row flags). */
 size_t regtr_kpconv_ws_bytes(int Nq, int Ns, int Cin);
+size_t regtr_kpconv_fwd_ws_bytes(int Nq, int Ns, int Cin, int Cout);
 int regtr_kpconv_fwd(const float* q, const float* s, const int32_t* idx, const float* x,
                      const float* W, const float* kp, int Nq, int Ns, const int32_t* nq_dev,
                      const int32_t* ns_dev, int K, int Cin, int Cout,

@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f'nvcc failed on {src}')
-    link = [nvcc, '-shared', '-o', LIB] + objs + ['-lcublas', '-Xlinker', '-rpath,/usr/local/cuda/lib64']
+    link = [nvcc, '-shared', '-o', LIB] + objs + ['-Xlinker', '-rpath,/usr/local/cuda/lib64']
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

@@ -5,10 +5,7 @@
 // Reference behaviour replaced (paths relative to /root/reference/src):
 //   models/backbone_kpconv/kpconv_blocks.py:269-414  KPConv.forward (rigid, linear, sum)
 //   models/backbone_kpconv/kpconv_blocks.py:127-143  max_pool
-#include <cublas_v2.h>
-
 #include <cstdlib>
-#include <mutex>
 
 #include "common.cuh"
 
@@ -518,20 +515,20 @@ __global__ void k_gemm_smallk(const float* __restrict__ a, const float* __restri
     *reinterpret_cast<float4*>(out + (size_t)r * Cout + c) = acc;
 }
 
-// ---- cuBLAS handle (one per device, created on first use)
-std::mutex g_mu;
-cublasHandle_t g_handles[64] = {};
-
-cublasHandle_t get_handle() {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) return nullptr;
-    std::lock_guard<std::mutex> lock(g_mu);
-    if (!g_handles[dev]) {
-        if (cublasCreate(&g_handles[dev]) != CUBLAS_STATUS_SUCCESS) return nullptr;
-        cublasSetMathMode(g_handles[dev], CUBLAS_PEDANTIC_MATH);   // fp32 parity path: no TF32
-    }
-    return g_handles[dev];
+// W[K, N] (row-major) -> TF32 (hi, lo) halves of W^T, [N, K] row-major: the B operand layout of the GEMM
+__global__ void k_split_transpose(const float* __restrict__ W, int K, int N, float* __restrict__ hi, float* __restrict__ lo) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)K * N) return;
+    const int n = (int)(t / K), k = (int)(t % K);
+    const float v = W[(size_t)k * N + n];
+    uint32_t u = __float_as_uint(v);
+    u += 0x0FFFu + ((u >> 13) & 1u);
+    const float h = __uint_as_float(u & 0xFFFFE000u);
+    float l = v - h;
+    uint32_t ul = __float_as_uint(l);
+    ul += 0x0FFFu + ((ul >> 13) & 1u);
+    hi[t] = h;
+    lo[t] = __uint_as_float(ul & 0xFFFFE000u);
 }
 
 size_t agg_smem_bytes(int K) {
@@ -591,9 +588,16 @@ bool agg_use_mma() {
 
 extern "C" {
 
+// wf | row flags  (what regtr_kpconv_aggregate needs; regtr_kpconv_fwd adds regtr_kpconv_fwd_ws_bytes)
 size_t regtr_kpconv_ws_bytes(int Nq, int Ns, int Cin) {
     return regtr_align(sizeof(float) * (size_t)(Nq > 0 ? Nq : 1) * KP * (size_t)Cin) +
            regtr_align((size_t)(Ns > 0 ? Ns : 1));
+}
+
+// + split W^T (hi, lo) + the GEMM's own workspace
+size_t regtr_kpconv_fwd_ws_bytes(int Nq, int Ns, int Cin, int Cout) {
+    const size_t w = regtr_align(sizeof(float) * (size_t)KP * (size_t)(Cin > 0 ? Cin : 1) * (size_t)(Cout > 0 ? Cout : 1));
+    return regtr_kpconv_ws_bytes(Nq, Ns, Cin) + 2 * w + regtr_gemm_ws_bytes(Nq, Cout, KP * Cin);
 }
 
 int regtr_kpconv_aggregate(const float* q, const float* s, const int32_t* idx, const float* x, const float* kp,
@@ -670,17 +674,21 @@ int regtr_kpconv_fwd(const float* q, const float* s, const int32_t* idx, const f
         REGTR_CHECK_LAUNCH();
         return REGTR_OK;
     }
-    // out[Nq,Cout] = wf[Nq,15*Cin] @ W[15*Cin,Cout]  (row-major)  ==  column-major out^T = W^T wf^T
-    // (library fallback of the C entry point; the Python path runs this contraction on k_gemm_tf32x3)
-    cublasHandle_t h = get_handle();
-    if (!h) return REGTR_ERR_CUBLAS;
-    if (cublasSetStream(h, st) != CUBLAS_STATUS_SUCCESS) return REGTR_ERR_CUBLAS;
-    const float one = 1.f, zero = 0.f;
+    // out[Nq,Cout] = wf[Nq,15*Cin] @ W[15*Cin,Cout] on the library's own 3xTF32 tcgen05 GEMM: split + transpose
+    // W into the workspace tail, then regtr_gemm_tf32x3 (the Python front end caches the split instead)
     const int KD = KP * Cin;
-    if (cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, Cout, Nq, KD, &one, W, Cout, wf, KD, &zero, out, Cout) !=
-        CUBLAS_STATUS_SUCCESS)
-        return REGTR_ERR_CUBLAS;
-    return REGTR_OK;
+    if (KD % 4) return REGTR_ERR_UNSUPPORTED;
+    char* p = (char*)ws + regtr_align(sizeof(float) * (size_t)Nq * KP * (size_t)Cin) + regtr_align((size_t)(Ns > 0 ? Ns : 1));
+    float* w_hi = (float*)p;
+    float* w_lo = (float*)(p + regtr_align(sizeof(float) * (size_t)KD * Cout));
+    void* gws = p + 2 * regtr_align(sizeof(float) * (size_t)KD * Cout);
+    const size_t used = (size_t)((char*)gws - (char*)ws);
+    const size_t gws_bytes = regtr_gemm_ws_bytes(Nq, Cout, KD);
+    if (ws_bytes < used + gws_bytes) return REGTR_ERR_WORKSPACE;
+    k_split_transpose<<<regtr_cdiv((long long)KD * Cout, 256), 256, 0, st>>>(W, KD, Cout, w_hi, w_lo);
+    REGTR_CHECK_LAUNCH();
+    return regtr_gemm_tf32x3(wf, KD, w_hi, w_lo, KD, out, Cout, nullptr, nullptr, 0, Nq, Cout, KD, nq_dev, 0, gws,
+                             gws_bytes, stream_);
 }
 
 int regtr_max_pool(const float* x, const int32_t* idx, int Nq, int Ns, const int32_t* ns_dev, int K, int C,

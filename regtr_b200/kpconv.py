@@ -23,6 +23,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .config import pyramid_plan
+from .lazy import LazyDict
 from .weights import kernel_disposition
 
 _CELL_SLACK = 1.0001   # cell = radius * slack: keeps |dx| < r inside the 27-cell stencil under fp32 rounding
@@ -47,11 +48,24 @@ class Pyramid:
     """Device-resident KPConv pyramid with capacity-shaped buffers.  Level sizes live in
     `offs_all[level]` (int32, device); nothing here requires a host synchronisation."""
 
-    def __init__(self, n_clouds, levels, caps, points, offs_all, conv32, conv64, pool32, pool64, up64, status):
+    def __init__(self, n_clouds, levels, caps, points, offs_all, conv32, conv64, pool32, pool64, up64, status,
+                 grids=None):
         self.n_clouds, self.levels, self.caps = n_clouds, levels, caps
         self.points, self.offs_all = points, offs_all
         self.conv32, self.conv64, self.pool32, self.pool64, self.up64 = conv32, conv64, pool32, pool64, up64
         self.status = status
+        self.grids = grids            # cell list per level (kept for the lazily computed `upsamples`)
+
+    def upsample_indices(self, li):
+        """`upsamples[li]` (kpconv.py:503-507): for every point of level li its first-K neighbours of level
+        li+1 inside radius 2 r_li, int64, capacity-shaped.  Computed on demand from the retained cell lists:
+        RegTR.forward never reads it."""
+        if self.up64[li] is None and self.levels[li]['strided']:
+            lvl = self.levels[li]
+            _, self.up64[li] = ops.ball_query(self.points[li], self.offs_all[li], self.points[li + 1],
+                                              self.offs_all[li + 1], self.grids[li + 1], lvl['K'], 2 * lvl['radius'],
+                                              q_order=self.grids[li].order, want32=False)
+        return self.up64[li]
 
     def n_dev(self, level):
         """1-element int32 device view holding the number of points of `level`."""
@@ -86,9 +100,11 @@ class PreprocessorGPU(nn.Module):
         self.compute_upsamples = compute_upsamples
 
     @torch.no_grad()
-    def build(self, points, offs0, n_clouds: int, caps=None, want64: bool = True) -> Pyramid:
+    def build(self, points, offs0, n_clouds: int, caps=None, want64: bool = True, upsamples: bool = None) -> Pyramid:
         """points (cap0,3) f32 packed clouds, offs0 (n_clouds+1) int32 device offsets.
-        caps: per-level row capacities (default: every level as large as level 0)."""
+        caps: per-level row capacities (default: every level as large as level 0).
+        upsamples: compute the `upsamples` lists (default: the module's `compute_upsamples`)."""
+        upsamples = self.compute_upsamples if upsamples is None else upsamples
         levels, _, _ = pyramid_plan(self.cfg)
         device = points.device
         cap0 = points.shape[0]
@@ -97,13 +113,14 @@ class PreprocessorGPU(nn.Module):
         status = ops.new_status(device)
         offs_all = torch.zeros((len(levels), n_clouds + 1), dtype=torch.int32, device=device)
         offs_all[0].copy_(offs0)
-        pts_l, conv32, conv64, pool32, pool64, up64 = [], [], [], [], [], []
+        pts_l, conv32, conv64, pool32, pool64, up64, grids = [], [], [], [], [], [], []
         cur = points
         grid = ops.CellGrid(cur, offs_all[0], n_clouds, levels[0]['radius'] * _CELL_SLACK, status)
         for li, lvl in enumerate(levels):
             r, K = lvl['radius'], lvl['K']
             offs = offs_all[li]
             pts_l.append(cur)
+            grids.append(grid)
             if lvl['has_conv']:
                 c32, c64 = ops.ball_query(cur, offs, cur, offs, grid, K, r, q_order=grid.order, want64=want64)
             else:
@@ -115,14 +132,14 @@ class PreprocessorGPU(nn.Module):
                 p32, p64 = ops.ball_query(nxt, offs_all[li + 1], cur, offs, grid, K, r, want64=want64)
                 nxt_grid = ops.CellGrid(nxt, offs_all[li + 1], n_clouds, 2 * r * _CELL_SLACK, status)
                 u64 = None
-                if self.compute_upsamples and want64 and 'bq_up' not in ops._ABLATE:
+                if upsamples and want64:
                     _, u64 = ops.ball_query(cur, offs, nxt, offs_all[li + 1], nxt_grid, K, 2 * r,
                                             q_order=grid.order, want32=False)
                 pool32.append(p32); pool64.append(p64); up64.append(u64)
                 cur, grid = nxt, nxt_grid
             else:
                 pool32.append(None); pool64.append(None); up64.append(None)
-        return Pyramid(n_clouds, levels, caps, pts_l, offs_all, conv32, conv64, pool32, pool64, up64, status)
+        return Pyramid(n_clouds, levels, caps, pts_l, offs_all, conv32, conv64, pool32, pool64, up64, status, grids)
 
     @staticmethod
     def check_status(code: int):
@@ -132,10 +149,11 @@ class PreprocessorGPU(nn.Module):
             raise RuntimeError('a pyramid level overflowed its static capacity')
 
     @staticmethod
-    def finalize(pyr: Pyramid, host=None):
+    def finalize(pyr: Pyramid, host=None, lazy_upsamples: bool = True):
         """The single host synchronisation: read the level sizes, narrow the capacity buffers to
         exact shapes and assemble the reference's dict.  `host` may carry an already-downloaded
-        (offs_all, status) pair."""
+        (offs_all, status) pair.  `upsamples` lists that the pyramid did not compute are produced on
+        first access of the key (LazyDict) unless lazy_upsamples=False."""
         n_clouds, levels = pyr.n_clouds, pyr.levels
         device = pyr.points[0].device
         if host is None:
@@ -147,9 +165,18 @@ class PreprocessorGPU(nn.Module):
         lens = [(offs_host[l, 1:] - offs_host[l, :-1]).tolist() for l in range(len(levels))]
         totals = [int(offs_host[l, -1]) for l in range(len(levels))]
         e_idx = torch.zeros((0, 1), dtype=torch.int64, device=device)
-        data = dict(points=[], neighbors=[], pools=[], upsamples=[], stack_lengths=[],
-                    _points=[], _offs=[], _neighbors32=[], _pools32=[], _lens=lens, _ndev=None,
-                    _n_clouds=n_clouds)
+        data = LazyDict(None, None, points=[], neighbors=[], pools=[], stack_lengths=[],
+                        _points=[], _offs=[], _neighbors32=[], _pools32=[], _lens=lens, _ndev=None,
+                        _n_clouds=n_clouds)
+
+        def upsamples():
+            ups = []
+            for li, lvl in enumerate(levels):
+                u = pyr.upsample_indices(li) if lvl['strided'] else None
+                ups.append(u[:totals[li]] if u is not None else e_idx)
+            return ups
+
+        lens_dev = (pyr.offs_all[:, 1:] - pyr.offs_all[:, :-1]).to(torch.int64)     # (levels, n_clouds), one tiny kernel
         for li, lvl in enumerate(levels):
             n = totals[li]
             data['points'].append(pyr.points[li][:n])
@@ -160,21 +187,24 @@ class PreprocessorGPU(nn.Module):
                 n2 = totals[li + 1]
                 data['pools'].append(pyr.pool64[li][:n2] if pyr.pool64[li] is not None else e_idx)
                 data['_pools32'].append(pyr.pool32[li][:n2])
-                data['upsamples'].append(pyr.up64[li][:n] if pyr.up64[li] is not None else e_idx)
             else:
                 data['pools'].append(e_idx)
                 data['_pools32'].append(None)
-                data['upsamples'].append(e_idx)
-            data['stack_lengths'].append(torch.tensor(lens[li], dtype=torch.int64).to(device, non_blocking=True))
+            data['stack_lengths'].append(lens_dev[li])
             data['_offs'].append(pyr.offs_all[li])
+        if lazy_upsamples:
+            data._lazy['upsamples'] = upsamples
+        else:
+            data['upsamples'] = upsamples()
         return data
 
     @torch.no_grad()
-    def forward(self, pts: List[torch.Tensor]):
+    def forward(self, pts: List[torch.Tensor], lazy_upsamples: bool = False):
         device = pts[0].device
         points = torch.cat([p.to(torch.float32) for p in pts], dim=0).contiguous()
         offs0 = ops.make_offsets([int(p.shape[0]) for p in pts], device)
-        return self.finalize(self.build(points, offs0, len(pts)))
+        pyr = self.build(points, offs0, len(pts), upsamples=False if lazy_upsamples else None)
+        return self.finalize(pyr, lazy_upsamples=lazy_upsamples)
 
 
 def _meta_private(meta, device):

@@ -1,8 +1,8 @@
 """ctypes binding of libregtr_b200.so (the C ABI declared in include/regtr_b200.h).
 
 The product path has NO fallback: if the CUDA library is missing or a call fails,
-`RegtrLibError` is raised.  torch must be imported before the library is loaded so that
-the already-loaded libcublas / libcudart are shared.
+`RegtrLibError` is raised.  torch is imported first so that its libcudart is the one in the process
+(the library links the CUDA runtime only -- no cuBLAS or other compute library).
 """
 from __future__ import annotations
 
@@ -10,7 +10,7 @@ import ctypes
 import os
 import re
 
-import torch  # noqa: F401  (loads libcudart / libcublas first)
+import torch  # noqa: F401  (loads libcudart first)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libregtr_b200.so')
@@ -38,6 +38,7 @@ SIGNATURES = {
     'regtr_cellgrid_build': (_I, [_P, _P, _I, _I, _F, _P, _P, _P, _P, _Z, _P]),
     'regtr_ball_query': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
     'regtr_kpconv_ws_bytes': (_Z, [_I, _I, _I]),
+    'regtr_kpconv_fwd_ws_bytes': (_Z, [_I, _I, _I, _I]),
     'regtr_kpconv_fwd': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _F, _P, _P, _Z, _P]),
     'regtr_kpconv_aggregate': (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _F, _P, _P, _I, _P]),
     'regtr_max_pool': (_I, [_P, _P, _I, _I, _P, _I, _I, _P, _P]),
@@ -60,7 +61,7 @@ SIGNATURES = {
 }
 
 _ERR = {-1: 'REGTR_ERR_ARG (rejected argument)', -2: 'REGTR_ERR_WORKSPACE (workspace too small)',
-        -3: 'REGTR_ERR_UNSUPPORTED (shape outside the hot path)', -4: 'REGTR_ERR_CUBLAS'}
+        -3: 'REGTR_ERR_UNSUPPORTED (shape outside the hot path)'}
 
 _lib = None
 

@@ -6,6 +6,8 @@ Tensors must live on a CUDA device; there is no CPU fallback.
 """
 from __future__ import annotations
 
+import contextlib
+import itertools
 import math
 
 import torch
@@ -14,16 +16,14 @@ from . import lib as _lib
 
 _ws_cache = {}
 
-# Diagnosis only (scripts/ablate.sh): REGTR_ABLATE=mha,agg,... skips a stage to measure its marginal cost
-# under multi-stream overlap.  Never set in tests or in the benchmark.
-import os as _os
-_ABLATE = set(filter(None, _os.environ.get('REGTR_ABLATE', '').split(',')))
-
 # Number of hand-written kernels (libregtr_b200.so, excluding CUB / cuBLAS) launched so far.
 LAUNCHES = 0
-# Optional profiler: when set to a list, ops.kpconv appends (cuda start event, end event, info dict)
-# around every KPConv call so that bench.py can time the dominant kernel on its own stream.
+# Optional profiler hooks (bench.py only): when KPCONV_TRACE is a list, ops.kpconv appends (cuda start event,
+# end event, info dict) around every KPConv call; when TRACE is a list, the GEMM / attention-core / gather
+# front ends append (kind, info dict, re-launch closure) so that the bench can re-time every launch of one
+# forward on its own (L2 flushed) and build per-kernel-family rooflines from the real shapes.
 KPCONV_TRACE = None
+TRACE = None
 
 
 def _count(n):
@@ -51,18 +51,48 @@ def _chk(t, dtype, name, dims=None):
     return t
 
 
-# Scratch buffers are shared by every call on a stream.  Executors that may run CONCURRENTLY on
-# different streams (pipelined CUDA graphs) set a private namespace while they capture, so that the
-# pointers baked into their graphs never alias another executor's scratch.
+# Scratch buffers.  Eager calls share one set per (device, CUDA stream): stream order makes the reuse
+# safe and two streams never alias each other's scratch (nor the self-resetting InstanceNorm counters).
+# A CUDA-graph capture runs under its own NAMESPACE token (`scratch_namespace`): the raw pointers baked into
+# that graph then belong to that graph alone; a buffer that has to grow inside a namespace keeps its
+# predecessor alive (`_ws_retired`) because an already captured graph may still write to it, and everything
+# is released together with `release_namespace` when the graph is dropped.
 WS_NAMESPACE = None
+_ws_retired = {}
+_ns_counter = itertools.count(1)
+
+
+def new_namespace():
+    return ('graph', next(_ns_counter))
+
+
+@contextlib.contextmanager
+def scratch_namespace(ns):
+    global WS_NAMESPACE
+    prev, WS_NAMESPACE = WS_NAMESPACE, ns
+    try:
+        yield ns
+    finally:
+        WS_NAMESPACE = prev
+
+
+def release_namespace(ns):
+    """Drop every scratch buffer of a namespace (call when its captured graph is destroyed)."""
+    for key in [k for k in _ws_cache if k[1] == ns]:
+        del _ws_cache[key]
+    _ws_retired.pop(ns, None)
 
 
 def workspace(nbytes: int, device, slot: str = 'default', zero: bool = False) -> torch.Tensor:
-    """Per-(device, namespace, slot) grow-only scratch buffer (stream-ordered reuse).
+    """Per-(device, namespace | stream, slot) grow-only scratch buffer (stream-ordered reuse).
     zero=True: allocated zero-filled (state that an op keeps zero between its own calls)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), WS_NAMESPACE, slot)
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    ns = WS_NAMESPACE if WS_NAMESPACE is not None else ('stream', torch.cuda.current_stream(device).cuda_stream)
+    key = (dev, ns, slot)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None and WS_NAMESPACE is not None:
+            _ws_retired.setdefault(ns, []).append(buf)      # a captured graph may hold this pointer
         n = max(int(nbytes * 1.25), 4096 if zero else 1 << 20)
         buf = (torch.zeros if zero else torch.empty)(n, dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
@@ -162,18 +192,25 @@ def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=No
     if P != 15 or kernel_points.shape != (15, 3) or Cin_w != Cin or q_pts.shape[0] != Nq or s_pts.shape[0] != Ns:
         raise ValueError('kpconv: inconsistent shapes')
     out = torch.empty((Nq, Cout), dtype=torch.float32, device=x.device) if out is None else out
-    nb = L.regtr_kpconv_ws_bytes(Nq, Ns, Cin)
+    nb = L.regtr_kpconv_fwd_ws_bytes(Nq, Ns, Cin, Cout) if Cin == 1 else L.regtr_kpconv_ws_bytes(Nq, Ns, Cin)
     ws = workspace(nb, x.device, 'kpconv')
     trace = KPCONV_TRACE
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if trace is not None else None
     if ev:
         ev[0].record()
-    if GEMM_BACKEND == 'tc3x' and (15 * Cin) % 4 == 0:
+    if Cin == 1:
+        # first block: gather + aggregation + the 15 x Cout contraction in one kernel (k_kpconv_c1)
+        _lib.check(L.regtr_kpconv_fwd(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(weights), _p(kernel_points), Nq, Ns,
+                                      _p(nq_dev), _p(ns_dev), K, Cin, Cout, float(extent), _p(out), _p(ws),
+                                      ws.numel(), _stream()), 'regtr_kpconv_fwd')
+        _count(1)
+    else:
         # gather/aggregate kernel, then the [Nq,15Cin] x [15Cin,Cout] contraction on the tensor cores
+        if (15 * Cin) % 4:
+            raise _lib.RegtrLibError(f'kpconv: Cin={Cin} breaks the 16-byte row pitch of the contraction (no fallback)')
         wf = ws[:Nq * 15 * Cin * 4].view(torch.float32).view(Nq, 15 * Cin)
         flags = row_flags if row_flags is not None else ws[regtr_align_up(Nq * 15 * Cin * 4):]
-        if 'agg' not in _ABLATE:
-          _lib.check(L.regtr_kpconv_aggregate(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(kernel_points), Nq, Ns,
+        _lib.check(L.regtr_kpconv_aggregate(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(kernel_points), Nq, Ns,
                                             _p(nq_dev), _p(ns_dev), K, Cin, float(extent), _p(wf), _p(flags),
                                             1 if row_flags is not None else 0, _stream()), 'regtr_kpconv_aggregate')
         _count(1 if row_flags is not None else 2)
@@ -182,11 +219,6 @@ def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=No
             ev[1].record()
             ev.append(True)
         gemm(wf, hi, lo, m_dev=nq_dev, out=out)
-    else:
-        _lib.check(L.regtr_kpconv_fwd(_p(q_pts), _p(s_pts), _p(idx32), _p(x), _p(weights), _p(kernel_points), Nq, Ns,
-                                      _p(nq_dev), _p(ns_dev), K, Cin, Cout, float(extent), _p(out), _p(ws),
-                                      ws.numel(), _stream()), 'regtr_kpconv_fwd')
-        _count(1 if Cin == 1 else 3)
     if ev:
         ev[2].record()
         trace.append((ev[0], ev[2], dict(Nq=Nq, Ns=Ns, K=K, Cin=Cin, Cout=Cout, idx=idx32,
@@ -232,12 +264,10 @@ def instnorm_act(x, offs, n_clouds: int, res=None, slope: float = -1.0, eps: flo
     if res is not None:
         _chk(res, torch.float32, 'res', 2)
     out = torch.empty_like(x) if out is None else out
-    if 'norm' in _ABLATE:
-        return out.copy_(x)
     nb = L.regtr_instnorm_ws_bytes(n, n_clouds, C)
     ws = workspace(nb, x.device, 'instnorm')
     flags = None
-    if want_flags and C // 4 <= 32 and (C // 4) & (C // 4 - 1) == 0 and 'norm' not in _ABLATE:
+    if want_flags and C // 4 <= 32 and (C // 4) & (C // 4 - 1) == 0:
         flags = torch.empty(max(n, 1), dtype=torch.uint8, device=x.device)
     # self-resetting completion counters: the last statistics block of a (cloud, channel tile) finalises it
     cnt = workspace(L.regtr_instnorm_counter_bytes(n_clouds, C), x.device, 'instnorm_cnt', zero=True)
@@ -278,10 +308,11 @@ def gemm(a, b_hi, b_lo, bias=None, residual=None, relu=False, m_dev=None, out=No
     M, K = a.shape
     N = b_hi.shape[0]
     out = torch.empty((M, N), dtype=torch.float32, device=a.device) if out is None else out
-    if 'gemm' in _ABLATE:
-        return out.zero_()
     nb = L.regtr_gemm_ws_bytes(M, N, K)
     ws = workspace(nb, a.device, 'gemm')
+    if TRACE is not None:
+        TRACE.append(('gemm', dict(M=M, N=N, K=K, split_k=nb > 256),
+                      lambda: gemm(a, b_hi, b_lo, bias=bias, residual=residual, relu=relu, m_dev=m_dev, out=out)))
     _lib.check(L.regtr_gemm_tf32x3(_p(a), a.stride(0), _p(b_hi), _p(b_lo), b_hi.stride(0), _p(out), out.stride(0),
                                    _p(bias), _p(residual), residual.stride(0) if residual is not None else 0,
                                    M, N, K, _p(m_dev), 1 if relu else 0, _p(ws), ws.numel(), _stream()),
@@ -290,21 +321,15 @@ def gemm(a, b_hi, b_lo, bias=None, residual=None, relu=False, m_dev=None, out=No
     return out
 
 
-# 'tc3x': hand-written tcgen05 3xTF32 GEMM (default);  'cublas': torch / cuBLAS fp32 SIMT sgemm
-GEMM_BACKEND = 'tc3x'
-
-
 def linear(x, weight, bias=None, residual=None, relu=False, m_dev=None):
-    """nn.Linear forward (x @ weight^T + bias) (+ residual, + ReLU).
-    Default: the 3xTF32 tcgen05 GEMM of this library (needs K % 4 == 0 for the TMA row pitch);
-    `GEMM_BACKEND = 'cublas'` or an unsupported K routes to cuBLAS as a plain library GEMM."""
-    if GEMM_BACKEND == 'tc3x' and x.shape[1] % 4 == 0 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0:
-        hi, lo = split_weight(weight)
-        return gemm(x, hi, lo, bias=bias, residual=residual, relu=relu, m_dev=m_dev)
-    y = torch.nn.functional.linear(x, weight, bias)
-    if residual is not None:
-        y = y + residual
-    return torch.relu_(y) if relu else y
+    """nn.Linear forward (x @ weight^T + bias) (+ residual, + ReLU) on the 3xTF32 tcgen05 GEMM of this
+    library.  The TMA row pitch needs K % 4 == 0 and 16-byte aligned rows; anything else raises (callers
+    with an odd K zero-pad it, see PositionEmbeddingLearned) -- there is no library fallback."""
+    if x.shape[1] % 4 or x.stride(0) % 4 or x.data_ptr() % 16:
+        raise _lib.RegtrLibError(f'linear: K={x.shape[1]}, row stride {x.stride(0)}: rows must be 16-byte '
+                                 'aligned multiples of 4 floats (zero-pad K); no cuBLAS fallback')
+    hi, lo = split_weight(weight)
+    return gemm(x, hi, lo, bias=bias, residual=residual, relu=relu, m_dev=m_dev)
 
 
 # -------------------------------------------------------------------- transformer
@@ -345,8 +370,6 @@ def layernorm_pos(x, gamma, beta, pos=None, eps: float = 1e-5, want_plain=True, 
     n, E = x.shape
     y = torch.empty_like(x) if want_plain else None
     yp = torch.empty_like(x) if want_pos else None
-    if 'ln' in _ABLATE:
-        return (y.copy_(x) if y is not None else None), (yp.copy_(x) if yp is not None else None)
     _lib.check(L.regtr_layernorm_pos(_p(x), _p(gamma), _p(beta), _p(pos), n, _p(n_dev), E, float(eps), _p(y), _p(yp),
                                      _stream()), 'regtr_layernorm_pos')
     _count(1)
@@ -391,8 +414,10 @@ def mha_varlen(q, k, v, q_start, q_len, k_start, k_len, max_q_len: int, n_heads:
     dh = E // n_heads
     # zeros: rows outside every problem (capacity padding) stay finite for the GEMMs downstream
     out = torch.zeros((q.shape[0], E), dtype=torch.float32, device=q.device) if out is None else out
-    if 'mha' in _ABLATE:
-        return out
+    if TRACE is not None:
+        ql, kl = q_len.tolist(), k_len.tolist()
+        TRACE.append(('mha', dict(pairs_qk=sum(a * b for a, b in zip(ql, kl)), E=E, tokens=sum(ql)),
+                      lambda: mha_varlen(q, k, v, q_start, q_len, k_start, k_len, max_q_len, n_heads, out=out)))
     _lib.check(L.regtr_mha_varlen_fwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
                                       out.stride(0), _p(q_start), _p(q_len), _p(k_start), _p(k_len),
                                       q_start.numel(), int(max_q_len), n_heads, dh, 1.0 / math.sqrt(dh), _stream()),

@@ -19,6 +19,7 @@ Training (`compute_loss`, autograd through the custom kernels) is a "next" row.
 from __future__ import annotations
 
 import logging
+import weakref
 
 import torch
 import torch.nn as nn
@@ -26,6 +27,7 @@ import torch.nn.functional as F
 
 from . import ops
 from .kpconv import KPFEncoder, PreprocessorGPU
+from .lazy import LazyDict
 from .transformer import (AttentionPlan, PositionEmbeddingCoordsSine, PositionEmbeddingLearned,
                           TransformerCrossEncoder, TransformerCrossEncoderLayer)
 
@@ -127,10 +129,12 @@ class RegTR(nn.Module):
         return next(self.parameters()).device
 
     # ------------------------------------------------------------------ core (sync-free)
-    def _core(self, meta, B: int, plan: AttentionPlan):
-        """Encoder -> projection -> position embedding -> cross-encoder -> regressor -> pose on
-        packed (possibly capacity-padded) rows.  No host synchronisation, CUDA-graph capturable."""
-        cfg = self.cfg
+    # The three stages after the pyramid, at the reference's own `_TIMEIT` boundaries (regtr.py:108-216:
+    # preprocess | encoder | attention + decoder | pose).  None synchronises with the host, so any prefix /
+    # suffix of them is CUDA-graph capturable (GraphedRegTR captures them as one graph, or one per stage
+    # when stage times are wanted).
+    def _stage_encoder(self, meta):
+        """KPConv encoder + feature projection + position embedding (regtr.py:122-154)."""
         pts = meta['_points']
         feats0 = torch.ones_like(pts[0][:, 0:1])                                   # regtr.py:122
         feats_un, _ = self.kpf_encoder(feats0, meta)                               # regtr.py:136
@@ -139,12 +143,26 @@ class RegTR(nn.Module):
                              m_dev=nd[-1] if nd else None)                         # regtr.py:145
         xyz_c = pts[-1]
         pe = self.pos_embed(xyz_c)                                                 # regtr.py:149-154
+        return dict(both_un=both_un.contiguous(), xyz_c=xyz_c, pe=pe)
+
+    def _stage_attention(self, enc, plan: AttentionPlan):
+        """Cross-encoder + correspondence decoder on all layers (regtr.py:156-183)."""
+        cfg = self.cfg
         cond = self.transformer_encoder.forward_packed(
-            both_un.contiguous(), pe if cfg.transformer_encoder_has_pos_emb else None, plan)   # (L,N,E)
-        corr, logit = self.correspondence_decoder.forward_packed(cond, xyz_c, pe, plan)   # regtr.py:168-171
-        # correspondences + sigmoid + weighted Kabsch, one launch (regtr.py:185-203)
-        pose = ops.pose_from_corr(xyz_c, corr.contiguous(), logit[..., 0].contiguous(), meta['_offs'][-1], B)
-        return dict(both_un=both_un, xyz_c=xyz_c, cond=cond, corr=corr, logit=logit, pose=pose)
+            enc['both_un'], enc['pe'] if cfg.transformer_encoder_has_pos_emb else None, plan)   # (L,N,E)
+        corr, logit = self.correspondence_decoder.forward_packed(cond, enc['xyz_c'], enc['pe'], plan)
+        return dict(cond=cond, corr=corr, logit=logit)
+
+    def _stage_pose(self, enc, att, offs_c, B: int):
+        """Correspondence assembly + sigmoid + weighted Kabsch, one launch (regtr.py:185-203)."""
+        return ops.pose_from_corr(enc['xyz_c'], att['corr'].contiguous(), att['logit'][..., 0].contiguous(), offs_c, B)
+
+    def _core(self, meta, B: int, plan: AttentionPlan):
+        enc = self._stage_encoder(meta)
+        att = self._stage_attention(enc, plan)
+        pose = self._stage_pose(enc, att, meta['_offs'][-1], B)
+        return dict(both_un=enc['both_un'], xyz_c=enc['xyz_c'], cond=att['cond'], corr=att['corr'],
+                    logit=att['logit'], pose=pose)
 
     @staticmethod
     def _assemble(core, lens_c, B):
@@ -174,7 +192,7 @@ class RegTR(nn.Module):
     def forward(self, batch):
         """Eager path: exact shapes, one host sync (pyramid sizes) before the encoder."""
         B = len(batch['src_xyz'])
-        meta = self.preprocessor(list(batch['src_xyz']) + list(batch['tgt_xyz']))    # regtr.py:117-118
+        meta = self.preprocessor(list(batch['src_xyz']) + list(batch['tgt_xyz']), lazy_upsamples=True)   # regtr.py:117-118
         batch['kpconv_meta'] = meta
         lens_c = meta['_lens'][-1]
         plan = AttentionPlan(lens_c, meta['_points'][-1].device)
@@ -184,34 +202,57 @@ class RegTR(nn.Module):
 class GraphedRegTR:
     """CUDA-graph executor of `RegTR.forward` for latency-bound serving (batch 1..B pairs).
 
-    The eager forward is launch-bound: ~370 kernels of a few microseconds each.
+    The eager forward is launch-bound: a few hundred kernels of a few microseconds each.
     Here the whole forward -- pyramid, encoder, cross-encoder, regressor, Kabsch -- is captured
     ONCE per (pairs, level-0 capacity bucket) into a CUDA graph over capacity-shaped buffers;
     data-dependent level sizes stay on the device (int32 offsets read by every kernel), so a
-    replay needs no host round trip.  Per call: one packed H2D/D2D copy of the points, one graph
-    launch, one small D2H (level sizes + status + pose) and a single synchronisation.
+    replay needs no host round trip.  Per call: one H2D/D2D copy per cloud into the packed buffer, one
+    graph launch, ONE small D2H (level sizes + status + pose) and a single synchronisation.
 
     Outputs are views into the graph's static buffers: valid until the next call with the same
-    bucket.  If a level overflows its static capacity (REGTR_STATUS_CAPACITY) the call falls back
-    to the eager forward, so results are never silently truncated.
+    bucket; the per-cloud views (and `batch['kpconv_meta']`) are built lazily on first access, `pose`
+    and `host_pose` (pinned host copy, not part of the reference contract) are always there.  If a
+    level overflows its static capacity (REGTR_STATUS_CAPACITY) the call falls back to the eager
+    forward, so results are never silently truncated.
+
+    `stages=True` captures the four `_TIMEIT` stages of the reference (regtr.py:108-216) as four graphs
+    replayed back to back with CUDA events in between: `stage_ms()` then reports where a pair's
+    latency goes (bench.py).  Every captured graph owns a private scratch namespace (ops.new_namespace):
+    no graph ever shares or outlives a buffer another graph writes.
     """
 
+    STAGES = ('preprocess', 'encoder', 'attention_decoder', 'pose')
+
     def __init__(self, model: RegTR, bucket: int = 8192, full_meta: bool = True, ratio: float = 0.30,
-                 retry_ratio: float = 0.45):
+                 retry_ratio: float = 0.45, stages: bool = False):
         self.model = model
         self.bucket = int(bucket)
         self.full_meta = full_meta
         self.ratio, self.retry_ratio = ratio, retry_ratio   # level-to-level capacity ratio (real data: 0.19-0.27)
+        self.stages = stages
         self.ratios = {}
         self.graphs = {}
         self.fallbacks = 0
+        weakref.finalize(self, GraphedRegTR._release_all, self.graphs)
+
+    @staticmethod
+    def _release_all(graphs):
+        for st in graphs.values():
+            ops.release_namespace(st['ns'])
+        graphs.clear()
+
+    def _drop(self, key):
+        st = self.graphs.pop(key, None)
+        if st is not None:
+            torch.cuda.synchronize(self.model.device)        # no replay of this graph is in flight any more
+            ops.release_namespace(st['ns'])
 
     def _capture(self, B: int, cap0: int):
-        prev_ns, ops.WS_NAMESPACE = ops.WS_NAMESPACE, id(self)       # private scratch for this executor's graphs
-        try:
-            return self._capture_impl(B, cap0)
-        finally:
-            ops.WS_NAMESPACE = prev_ns
+        ns = ops.new_namespace()                 # private scratch for THIS graph (never freed while it lives)
+        with ops.scratch_namespace(ns):
+            st = self._capture_impl(B, cap0)
+        st['ns'] = ns
+        return st
 
     def _capture_impl(self, B: int, cap0: int):
         from .kpconv import level_capacities
@@ -220,35 +261,73 @@ class GraphedRegTR:
         caps = level_capacities(model.cfg, cap0, ratio=self.ratios.get((B, cap0), self.ratio))
         st = dict(points=torch.zeros((cap0, 3), dtype=torch.float32, device=dev),
                   offs0=torch.zeros(2 * B + 1, dtype=torch.int32, device=dev), caps=caps)
+        box = {}
+
+        def s_pre():
+            box['pyr'] = model.preprocessor.build(st['points'], st['offs0'], 2 * B, caps=caps,
+                                                  want64=self.full_meta, upsamples=False)
+            box['plan'] = AttentionPlan.from_device(box['pyr'].offs_all[-1], B, caps[-1])
+            box['meta'] = box['pyr'].private(static=True)
+
+        def s_enc():
+            box['enc'] = model._stage_encoder(box['meta'])
+
+        def s_att():
+            box['att'] = model._stage_attention(box['enc'], box['plan'])
+
+        def s_pose():
+            pyr = box['pyr']
+            box['pose'] = model._stage_pose(box['enc'], box['att'], box['meta']['_offs'][-1], B)
+            # everything the host needs, in ONE buffer / one D2H: level offsets | status | pose bits
+            box['tail'] = torch.cat([pyr.offs_all.reshape(-1), pyr.status.view(torch.int32),
+                                     box['pose'].reshape(-1).view(torch.int32)])
+
+        fns = [s_pre, s_enc, s_att, s_pose]
 
         def run():
-            pyr = model.preprocessor.build(st['points'], st['offs0'], 2 * B, caps=caps, want64=self.full_meta)
-            plan = AttentionPlan.from_device(pyr.offs_all[-1], B, caps[-1])
-            core = model._core(pyr.private(static=True), B, plan)
-            tail = torch.cat([pyr.offs_all.reshape(-1), pyr.status])
-            return pyr, core, tail
+            for f in fns:
+                f()
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):           # warm-up (sizes workspaces, cuBLAS, caches) before capture
-            # a plausible offset table so that the warm-up exercises every kernel
-            n = cap0 // (2 * B)
+        with torch.cuda.stream(side):           # warm-up (sizes the scratch buffers, caches) before capture
+            n = cap0 // (2 * B)                 # a plausible offset table so that the warm-up exercises every kernel
             st['offs0'].copy_(torch.arange(0, 2 * B + 1, dtype=torch.int32, device=dev) * n)
             st['points'].uniform_(-1.0, 1.0)
             for _ in range(2):
                 run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        g = torch.cuda.CUDAGraph()
         n0 = ops.LAUNCHES
-        with torch.cuda.graph(g):
-            pyr, core, tail = run()
-        st['n_launches'] = ops.LAUNCHES - n0       # hand-written kernels per replay (for launch accounting)
-        st.update(graph=g, pyr=pyr, core=core, tail=tail,
-                  tail_host=torch.empty(tail.numel(), dtype=torch.int32).pin_memory(),
-                  pose_host=torch.empty(tuple(core['pose'].shape), dtype=torch.float32).pin_memory(),
+        graphs = []
+        if self.stages:
+            pool = None
+            for f in fns:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    f()
+                pool = pool or g.pool()
+                graphs.append(g)
+        else:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run()
+            graphs.append(g)
+        pyr, tail = box['pyr'], box['tail']
+        core = dict(both_un=box['enc']['both_un'], xyz_c=box['enc']['xyz_c'], cond=box['att']['cond'],
+                    corr=box['att']['corr'], logit=box['att']['logit'], pose=box['pose'])
+        n_tail = tail.numel()
+        tail_host = torch.empty(n_tail, dtype=torch.int32).pin_memory()
+        n_meta = pyr.offs_all.numel() + 1
+        st.update(graphs=graphs, pyr=pyr, core=core, tail=tail, tail_host=tail_host,
+                  n_launches=ops.LAUNCHES - n0,           # hand-written kernels per replay (launch accounting)
+                  tail_np=tail_host.numpy(), n_meta=n_meta,
+                  host_pose=tail_host[n_meta:].view(torch.float32).view(tuple(core['pose'].shape)),
                   offs_host=torch.empty(2 * B + 1, dtype=torch.int32).pin_memory(),
-                  done=torch.cuda.Event())
+                  done=torch.cuda.Event(),
+                  stage_ev=[torch.cuda.Event(enable_timing=True) for _ in range(len(fns) + 1)]
+                  if self.stages else None)
+        st['offs_np'] = st['offs_host'].numpy()
         return st
 
     @torch.no_grad()
@@ -256,58 +335,78 @@ class GraphedRegTR:
         """Enqueue one forward on the current stream (no host synchronisation): copy the clouds into the
         static buffers, replay the graph, start the D2H of (level sizes, status, pose).  Returns a ticket
         for `result`."""
-        model = self.model
-        dev = model.device
-        src, tgt = list(batch['src_xyz']), list(batch['tgt_xyz'])
+        src, tgt = batch['src_xyz'], batch['tgt_xyz']
         B = len(src)
-        clouds = src + tgt
-        lens0 = [int(c.shape[0]) for c in clouds]
+        clouds = list(src) + list(tgt)
+        lens0 = [c.shape[0] for c in clouds]
         n0 = sum(lens0)
         cap0 = max(self.bucket, (n0 + self.bucket - 1) // self.bucket * self.bucket)
         key = (B, cap0)
         st = self.graphs.get(key)
         if st is None:
             st = self.graphs[key] = self._capture(B, cap0)
-        offs = [0]
-        for v in lens0:
-            offs.append(offs[-1] + v)
-        if clouds[0].is_cuda:
-            torch.cat(clouds, dim=0, out=st['points'][:n0])
-        else:                                   # host clouds: asynchronous H2D straight into the packed buffer
-            for c, a in zip(clouds, offs):      # (pinned sources copy without a staging pass)
-                st['points'][a:a + c.shape[0]].copy_(c, non_blocking=True)
-        st['offs_host'].copy_(torch.tensor(offs, dtype=torch.int32))
+        offs = st['offs_np']
+        a = 0
+        pts = st['points']
+        for i, c in enumerate(clouds):          # H2D (pinned sources: asynchronous, no staging pass) or D2D
+            offs[i] = a
+            pts[a:a + lens0[i]].copy_(c, non_blocking=True)
+            a += lens0[i]
+        offs[2 * B] = a
         st['offs0'].copy_(st['offs_host'], non_blocking=True)
-        st['graph'].replay()
+        if st['stage_ev'] is None:
+            st['graphs'][0].replay()
+        else:
+            ev = st['stage_ev']
+            ev[0].record()
+            for g, e in zip(st['graphs'], ev[1:]):
+                g.replay()
+                e.record()
         ops.LAUNCHES += st['n_launches']
         st['tail_host'].copy_(st['tail'], non_blocking=True)
-        st['pose_host'].copy_(st['core']['pose'], non_blocking=True)
-        st['done'].record(torch.cuda.current_stream(dev))
+        st['done'].record()
         return (key, st, batch, B)
+
+    def stage_ms(self, key=None):
+        """{stage: milliseconds} of the LAST finished replay (stages=True executors only)."""
+        st = self.graphs[key] if key is not None else next(iter(self.graphs.values()))
+        ev = st['stage_ev']
+        return {nm: ev[i].elapsed_time(ev[i + 1]) for i, nm in enumerate(self.STAGES)}
 
     @torch.no_grad()
     def result(self, ticket):
-        """Wait for a submitted forward and assemble the reference's output dict (views into the graph's
+        """Wait for a submitted forward and return the reference's output dict (views into the graph's
         static buffers: valid until the next submit on the same capacity bucket)."""
         key, st, batch, B = ticket
         model = self.model
         st['done'].synchronize()
         pyr = st['pyr']
         n_lvl = len(pyr.levels)
-        host = st['tail_host']
-        code = int(host[-1])
+        n_meta = st['n_meta']
+        code = int(st['tail_np'][n_meta - 1])
         if code & 2:                            # a level overflowed its capacity: redo eagerly and
             self.fallbacks += 1                 # re-capture this bucket with more head-room next time
             if self.ratios.get(key, self.ratio) < self.retry_ratio:
                 self.ratios[key] = self.retry_ratio
-                self.graphs.pop(key, None)
-            return model.forward(batch)
-        offs_host = host[:-1].reshape(n_lvl, 2 * B + 1)
-        meta = model.preprocessor.finalize(pyr, host=(offs_host, code))
+                self._drop(key)
+            dev = model.device                  # the eager forward has no host path: move host clouds first
+            eager = {k: [c.to(dev, non_blocking=True) for c in batch[k]] for k in ('src_xyz', 'tgt_xyz')}
+            out = model.forward(eager)
+            batch['kpconv_meta'] = eager['kpconv_meta']
+            out['host_pose'] = out['pose'].cpu()
+            return out
+        offs_np = st['tail_np'][:n_meta - 1].copy()          # this call's level sizes (the pinned buffer is reused)
+
+        def make_meta():
+            return model.preprocessor.finalize(pyr, host=(torch.from_numpy(offs_np).reshape(n_lvl, 2 * B + 1), code))
+
+        meta = LazyDict(make_meta)
         batch['kpconv_meta'] = meta
-        out = model._assemble(st['core'], meta['_lens'][-1], B)
-        out['pose_host'] = st['pose_host']
-        return out
+
+        def make_out():
+            return model._assemble(st['core'], meta['_lens'][-1], B)
+
+        return LazyDict(make_out, pose=st['core']['pose'], host_pose=st['host_pose'])
 
     def __call__(self, batch):
         return self.result(self.submit(batch))

@@ -1,18 +1,28 @@
-"""A few graph replays of the default bench workload (for ncu launch lists / profiles)."""
-import sys, os
+"""A few graph replays of the bench workload (for ncu launch lists / profiles).
+
+    python scripts/replay_loop.py [n_rep] [pairs_per_step] [config]
+"""
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+
 from regtr_b200.config import get_config
 from regtr_b200.regtr import GraphedRegTR, RegTR
-from regtr_b200.synthetic import make_3dmatch_pair
+from regtr_b200.synthetic import make_batch
 from regtr_b200.weights import random_state_dict
+
 DEV = 'cuda:0'
 n_rep = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+config = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 cfg = get_config('3dmatch')
-model = RegTR(cfg).to(DEV).eval(); model.load_state_dict(random_state_dict(cfg, 2024), strict=True)
+model = RegTR(cfg).to(DEV).eval()
+model.load_state_dict(random_state_dict(cfg, 2024), strict=True)
 runner = GraphedRegTR(model)
-p = make_3dmatch_pair(2000)
-b = {'src_xyz': [torch.from_numpy(p['src_xyz']).to(DEV)], 'tgt_xyz': [torch.from_numpy(p['tgt_xyz']).to(DEV)]}
+b = make_batch(config, B)
+b = {k: [torch.from_numpy(c).to(DEV) for c in b[k]] for k in ('src_xyz', 'tgt_xyz')}
 for _ in range(n_rep):
     out = runner(dict(b))
 torch.cuda.synchronize()

@@ -15,7 +15,9 @@ large float tensors plus their fp64 checksums.
 """
 from __future__ import annotations
 
+import hashlib
 import os
+import re
 import sys
 
 import numpy as np
@@ -48,8 +50,86 @@ FORWARD_CASES = {
 }
 
 
+# The reference's own sample inputs (src/demo.py:154-192 runs exactly these files): real 3DMatch fragments sit
+# on a 6 mm sensor lattice where voxel-boundary hits are common, which no synthetic cloud
+# exercises.  The clouds are copied (fp32: the files hold fp32 values stored as fp64, the demo casts with
+# .float()) into tests/golden/real/ as INPUT fixtures; outputs come from the unmodified reference.
+REF_DATA = '/root/reference/data'
+REAL_CASES = {
+    'real_3dmatch_redkitchen_0_5': ('3dmatch', 31, 'indoor/test/7-scenes-redkitchen/cloud_bin_0.pth',
+                                    'indoor/test/7-scenes-redkitchen/cloud_bin_5.pth'),
+    'real_3dmatch_sun3d_home_38_41': ('3dmatch', 32,
+                                      'indoor/test/sun3d-home_at-home_at_scan1_2013_jan_1/cloud_bin_38.pth',
+                                      'indoor/test/sun3d-home_at-home_at_scan1_2013_jan_1/cloud_bin_41.pth'),
+    'real_3dmatch_sun3d_hotel3_8_15': ('3dmatch', 33, 'indoor/test/sun3d-hotel_umd-maryland_hotel3/cloud_bin_8.pth',
+                                       'indoor/test/sun3d-hotel_umd-maryland_hotel3/cloud_bin_15.pth'),
+    'real_modelnet_2': ('modelnet', 34, 'modelnet_demo_data/modelnet_test_2_0.ply',
+                        'modelnet_demo_data/modelnet_test_2_1.ply'),
+    'real_modelnet_630': ('modelnet', 35, 'modelnet_demo_data/modelnet_test_630_0.ply',
+                          'modelnet_demo_data/modelnet_test_630_1.ply'),
+}
+
+
 def _np(t):
     return t.detach().cpu().numpy()
+
+
+def load_point_cloud(fname):
+    """demo.py:140-151 without open3d: .pth = pickled ndarray, .ply = binary little-endian xyz doubles."""
+    if fname.endswith('.pth'):
+        data = torch.load(fname, weights_only=False)
+    else:
+        raw = open(fname, 'rb').read()
+        head, body = raw.split(b'end_header\n', 1)
+        assert b'format binary_little_endian' in head and b'property double x' in head
+        n = int(re.search(rb'element vertex (\d+)', head).group(1))
+        data = np.frombuffer(body, dtype='<f8', count=3 * n).reshape(n, 3)
+    return np.asarray(data)[:, :3]
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+def real_fixture(name):
+    """Forward of the unmodified reference on one of its own sample pairs.  Keeps the fixture small: exact
+    level sizes and level >= 1 points, SHA-256 (+ a strided row sample) of every int64 index array, strided
+    feature rows with fp64 checksums, correspondences, overlap logits and poses in full."""
+    cfg_name, wseed, src_rel, tgt_rel = REAL_CASES[name]
+    cfg = get_config(cfg_name)
+    sd = random_state_dict(cfg, wseed)
+    src = load_point_cloud(os.path.join(REF_DATA, src_rel)).astype(np.float32)   # demo.py:180 `.float()`
+    tgt = load_point_cloud(os.path.join(REF_DATA, tgt_rel)).astype(np.float32)
+    os.makedirs(os.path.join(OUT, 'real'), exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, 'real', name + '_input.npz'), src_xyz=src, tgt_xyz=tgt,
+                        src_file=np.array(src_rel), tgt_file=np.array(tgt_rel))
+    model = ref_bridge.build_reference_model(cfg, sd)
+    out = ref_bridge.reference_forward(model, [src], [tgt])
+    meta = out['kpconv_meta']
+    step = 13
+    fx = {'pose': _np(out['pose']), 'row_step': np.array(step)}
+    for lvl in range(len(meta['points'])):
+        fx[f'stack_lengths_{lvl}'] = _np(meta['stack_lengths'][lvl]).astype(np.int64)
+        for key in ('neighbors', 'pools', 'upsamples'):
+            a = _np(meta[key][lvl]).astype(np.int64)
+            fx[f'{key}_{lvl}_shape'] = np.array(a.shape, dtype=np.int64)
+            fx[f'{key}_{lvl}_sha256'] = sha(a)
+            fx[f'{key}_{lvl}_rows'] = a[::97].astype(np.int32)
+        if lvl > 0:
+            fx[f'points_{lvl}'] = _np(meta['points'][lvl])
+    for side in ('src', 'tgt'):
+        fx[f'{side}_kp_warped_0'] = _np(out[f'{side}_kp_warped'][0])
+        fx[f'{side}_overlap_0'] = _np(out[f'{side}_overlap'][0])
+        fu, fc = _np(out[f'{side}_feat_un'][0]), _np(out[f'{side}_feat'][0])
+        fx[f'{side}_feat_un_0_rows'] = fu[::step]
+        fx[f'{side}_feat_0_rows'] = fc[:, ::step]
+        fx[f'{side}_feat_un_0_sum'] = np.array(fu.astype(np.float64).sum())
+        fx[f'{side}_feat_0_sum'] = np.array(fc.astype(np.float64).sum())
+        fx[f'{side}_feat_un_0_absmax'] = np.array(np.abs(fu).max())
+        fx[f'{side}_feat_0_absmax'] = np.array(np.abs(fc).max())
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), **fx)
+    print(name, [int(fx[f'stack_lengths_{l}'].sum()) for l in range(len(meta['points']))],
+          'pose[-1]', fx['pose'][-1, 0, 0])
 
 
 def forward_fixture(name):
@@ -252,11 +332,17 @@ def loss_fixture():
 if __name__ == '__main__':
     torch.manual_seed(0)
     np.random.seed(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'real':          # only the real-data fixtures (minutes of CPU)
+        for case in (sys.argv[2:] or REAL_CASES):
+            real_fixture(case)
+        sys.exit(0)
     eval_fixtures()
     loss_fixture()
     op_fixtures()
     for case in FORWARD_CASES:
         forward_fixture(case)
+    for case in REAL_CASES:
+        real_fixture(case)
     for f in sorted(os.listdir(OUT)):
         if f.endswith('.npz'):
             print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, 'KiB')

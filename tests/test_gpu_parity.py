@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import FORWARD_CASES, VARIANT_CASES, check_forward_against_golden, load_golden, make_case
+from conftest import (FORWARD_CASES, REAL_CASES, VARIANT_CASES, check_forward_against_golden,
+                      check_real_forward_against_golden, load_golden, make_case, make_real_case)
 
 pytestmark = pytest.mark.gpu
 
@@ -372,17 +373,21 @@ def test_graphed_executor_matches_eager_and_survives_overflow():
         s = float(want['src_feat'][0].abs().max())
         assert float((got['src_feat'][0] - want['src_feat'][0]).abs().max()) <= 2e-5 * s
         assert float((got['pose'] - want['pose']).abs().max()) <= 5e-5     # two fp32-accurate evaluation orders
-        assert torch.equal(got['pose_host'], got['pose'].cpu())
+        assert torch.equal(got['host_pose'], got['pose'].cpu())
     assert len(runner.graphs) == 1 and runner.fallbacks == 0
     # volume-filling cloud: every point its own voxel -> level 1 does not fit 0.4 * cap0 -> eager fallback
     rng = np.random.default_rng(0)
     src = rng.uniform(-2, 2, size=(7000, 3)).astype(np.float32)
     tgt = rng.uniform(-2, 2, size=(7000, 3)).astype(np.float32)
     b_e = {'src_xyz': [G(src)], 'tgt_xyz': [G(tgt)]}
-    b_g = {'src_xyz': [G(src)], 'tgt_xyz': [G(tgt)]}
+    b_g = {'src_xyz': [torch.from_numpy(src).pin_memory()], 'tgt_xyz': [torch.from_numpy(tgt).pin_memory()]}   # HOST clouds
     want, got = model(b_e), runner(b_g)
     assert runner.fallbacks == 1
-    assert torch.equal(got['pose'], want['pose'])
+    assert torch.equal(got['pose'], want['pose']) and torch.equal(got['host_pose'], want['pose'].cpu())
+    assert torch.equal(b_g['kpconv_meta']['neighbors'][1], b_e['kpconv_meta']['neighbors'][1])
+    # the bucket was re-captured with more head-room (its old graph and scratch released): next call is a replay
+    got2 = runner({'src_xyz': [G(src)], 'tgt_xyz': [G(tgt)]})
+    assert runner.fallbacks == 1 and float((got2['pose'] - want['pose']).abs().max()) <= 5e-5
 
 
 def test_tcgen05_attention_core_vs_fp32_kernel():
@@ -454,8 +459,8 @@ def test_pipelined_executor_matches_serial():
     for b in batches():
         done = pipe.submit(b)
         if done is not None:
-            got.append(done['pose_host'].clone())
-    got += [o['pose_host'].clone() for o in pipe.drain()]
+            got.append(done['host_pose'].clone())
+    got += [o['host_pose'].clone() for o in pipe.drain()]
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert torch.equal(a, b)
@@ -483,3 +488,170 @@ def test_graphed_executor_batch_of_two_pairs():
         assert got['src_kp'][b].shape == want['src_kp'][b].shape and torch.equal(got['src_kp'][b], want['src_kp'][b])
         assert got['src_overlap'][b].shape == want['src_overlap'][b].shape
     assert [int(v) for v in b_g['kpconv_meta']['stack_lengths'][0]] == [len(p['src_xyz']) for p in ps] + [len(p['tgt_xyz']) for p in ps]
+
+
+# ------------------------------------------------- the reference's own sample clouds (real data)
+
+@pytest.mark.parametrize('case', sorted(REAL_CASES))
+def test_forward_real_pairs_vs_reference_golden(case):
+    """The inputs src/demo.py:154-192 runs -- real 3DMatch fragments (6 mm sensor lattice: voxel-boundary hits
+    are common) and the ModelNet demo plys -- through the CUDA path, against the unmodified
+    reference: level sizes, coarse points and all neighbour indices bit-exact (SHA-256), features 1e-4, pose 1e-4."""
+    cfg, sd, src, tgt = make_real_case(case)
+    out, meta = _run_model(cfg, sd, [src], [tgt])
+    check_real_forward_against_golden(out, meta, load_golden(case), feat_rtol=1e-4, corr_atol=1e-4,
+                                      logit_atol=2e-4, pose_atol=1e-4)
+
+
+def test_real_pair_through_graph_executor_host_inputs():
+    """Same, through the CUDA-graph executor with pinned HOST clouds (the serving path of bench.py's e2e leg)."""
+    from regtr_b200.regtr import GraphedRegTR, RegTR
+    case = 'real_3dmatch_redkitchen_0_5'
+    cfg, sd, src, tgt = make_real_case(case)
+    model = RegTR(cfg).to(DEV).eval()
+    model.load_state_dict(sd, strict=True)
+    runner = GraphedRegTR(model)
+    batch = {'src_xyz': [torch.from_numpy(src).pin_memory()], 'tgt_xyz': [torch.from_numpy(tgt).pin_memory()]}
+    out = runner(batch)
+    assert runner.fallbacks == 0
+    check_real_forward_against_golden(out, batch['kpconv_meta'], load_golden(case), feat_rtol=1e-4, corr_atol=1e-4,
+                                      logit_atol=2e-4, pose_atol=1e-4)
+    assert torch.equal(out['host_pose'], out['pose'].cpu())
+
+
+# ------------------------------------------------- BASELINE configs 3 / 4 (8 pairs per GPU per step) and 5
+
+def _oracle_pose_and_meta(cfg, sd, p):
+    from oracle import pre, regtr_oracle as O
+    want = pre.preprocess(cfg, [p['src_xyz'], p['tgt_xyz']])
+    return O.forward(sd, cfg, [p['src_xyz']], [p['tgt_xyz']], meta=want), want
+
+
+def test_config3_batch8_full_size_vs_oracle():
+    """BASELINE config 3 / the per-GPU share of config 4: 8 full-size (~20k-point) pairs in ONE forward through
+    the CUDA-graph executor, fp32 parity mode.  Every pair is independent, so each is checked
+    against the oracle run on that pair alone: indices exact, features 1e-4, pose 1e-4."""
+    from regtr_b200.config import get_config
+    from regtr_b200.regtr import GraphedRegTR, RegTR
+    from regtr_b200.synthetic import make_batch
+    from regtr_b200.weights import random_state_dict
+    cfg = get_config('3dmatch')
+    sd = random_state_dict(cfg, 5)
+    model = RegTR(cfg).to(DEV).eval()
+    model.load_state_dict(sd, strict=True)
+    B = 8
+    b = make_batch(3, B)
+    batch = {'src_xyz': [G(a) for a in b['src_xyz']], 'tgt_xyz': [G(a) for a in b['tgt_xyz']]}
+    runner = GraphedRegTR(model)
+    out = runner(batch)
+    assert runner.fallbacks == 0 and out['pose'].shape == (6, B, 3, 4)
+    meta = batch['kpconv_meta']
+    n_lvl = len(meta['points'])
+    lens = [[int(v) for v in meta['stack_lengths'][l]] for l in range(n_lvl)]
+    starts = [np.concatenate([[0], np.cumsum(l)]) for l in lens]
+    for i in (0, 3, 7):                                         # three of the eight pairs against the oracle
+        p = {k: b[k][i] for k in ('src_xyz', 'tgt_xyz')}
+        ref, want = _oracle_pose_and_meta(cfg, sd, p)
+        for l in range(n_lvl):
+            assert [lens[l][i], lens[l][B + i]] == [int(v) for v in want['stack_lengths'][l]], (i, l)
+            # the pair's rows inside the stacked level: src block i, tgt block B + i; indices are stack-relative
+            for blk, (lo_w, hi_w) in ((i, (0, lens[l][i])), (B + i, (lens[l][i], lens[l][i] + lens[l][B + i]))):
+                rows = slice(starts[l][blk], starts[l][blk + 1])
+                assert np.array_equal(N(meta['points'][l][rows]), want['points'][l][lo_w:hi_w]), (i, l, 'points')
+                got = N(meta['neighbors'][l][rows])
+                w = want['neighbors'][l][lo_w:hi_w]
+                shadow_g, shadow_w = sum(lens[l]), want['points'][l].shape[0]
+                # map stack-relative ids to cloud-relative ones on both sides (shadow -> -1)
+                g_rel = np.where(got == shadow_g, -1, got - starts[l][blk])
+                w_rel = np.where(w == shadow_w, -1, w - lo_w)
+                assert np.array_equal(g_rel, w_rel), (i, l, 'neighbors')
+        for side in ('src', 'tgt'):
+            a, r = N(out[f'{side}_feat'][i]), ref[f'{side}_feat'][0].numpy()
+            assert np.abs(a - r).max() <= 1e-4 * np.abs(r).max(), (i, side)
+        assert np.abs(N(out['pose'][:, i]) - ref['pose'][:, 0].numpy()).max() <= 1e-4, i
+    R = N(out['pose'])[..., :3].astype(np.float64)               # all 8: proper rotations on every layer
+    assert np.abs(R @ np.swapaxes(R, -1, -2) - np.eye(3)).max() <= 1e-5 and np.all(np.linalg.det(R) > 0)
+
+
+def test_config5_lomatch_30k_pair_vs_oracle():
+    """BASELINE config 5: a ~30k-point low-overlap (10-30 %) pair -- a new level-0 capacity bucket and denser
+    K-truncation -- eager and through the graph executor, against the oracle: indices exact, pose 1e-4."""
+    from regtr_b200.config import get_config
+    from regtr_b200.regtr import GraphedRegTR, RegTR
+    from regtr_b200.synthetic import make_batch
+    from regtr_b200.weights import random_state_dict
+    cfg = get_config('3dmatch')
+    sd = random_state_dict(cfg, 5)
+    b = make_batch(5, 1)
+    p = {k: b[k][0] for k in ('src_xyz', 'tgt_xyz')}
+    assert 25000 <= len(p['src_xyz']) <= 36000
+    ref, want = _oracle_pose_and_meta(cfg, sd, p)
+    model = RegTR(cfg).to(DEV).eval()
+    model.load_state_dict(sd, strict=True)
+    runner = GraphedRegTR(model)
+    for run in (model, runner):
+        batch = {'src_xyz': [G(p['src_xyz'])], 'tgt_xyz': [G(p['tgt_xyz'])]}
+        out = run(batch)
+        meta = batch['kpconv_meta']
+        for key in ('points', 'neighbors', 'pools', 'stack_lengths'):
+            for lvl, (a, w) in enumerate(zip(meta[key], want[key])):
+                assert np.array_equal(N(a), w), f'{key}[{lvl}]'
+        for k in ('src_feat', 'tgt_feat'):
+            a, r = N(out[k][0]), ref[k][0].numpy()
+            assert np.abs(a - r).max() <= 1e-4 * np.abs(r).max(), k
+        assert np.abs(N(out['pose']) - ref['pose'].numpy()).max() <= 1e-4
+    assert runner.fallbacks == 0
+    trunc = float((N(meta['neighbors'][0])[:, -1] < want['points'][0].shape[0]).mean())
+    assert trunc > 0.02                                          # the K=40 truncation regime is exercised
+
+
+def test_two_capacity_buckets_on_one_runner_keep_their_scratch():
+    """One executor, two level-0 capacity buckets (8192-point and 16384-point graphs): capturing the larger
+    graph must not free or alias the scratch the smaller graph's replay writes (every captured graph owns a
+    private scratch namespace).  The small bucket is replayed AFTER the large one was captured and after
+    unrelated allocations recycled the caching allocator's free blocks."""
+    from regtr_b200.config import get_config
+    from regtr_b200.regtr import GraphedRegTR, RegTR
+    from regtr_b200.synthetic import make_3dmatch_pair
+    from regtr_b200.weights import random_state_dict
+    cfg = get_config('3dmatch')
+    model = RegTR(cfg).to(DEV).eval()
+    model.load_state_dict(random_state_dict(cfg, 12), strict=True)
+    small = [make_3dmatch_pair(2600 + i, 3000 + 200 * i) for i in range(2)]
+    large = make_3dmatch_pair(2610, 6500)
+    mk = lambda p: {'src_xyz': [G(p['src_xyz'])], 'tgt_xyz': [G(p['tgt_xyz'])]}
+    want_small = [model(mk(p))['pose'].clone() for p in small]
+    want_large = model(mk(large))['pose'].clone()
+    runner = GraphedRegTR(model, bucket=8192)
+    got0 = runner(mk(small[0]))['pose'].clone()
+    gotL = runner(mk(large))['pose'].clone()
+    assert len(runner.graphs) == 2 and runner.fallbacks == 0
+    junk = [torch.full((1 << 22,), float('nan'), device=DEV) for _ in range(8)]     # churn the allocator
+    del junk
+    torch.cuda.empty_cache()
+    got1 = runner(mk(small[1]))['pose'].clone()
+    got0b = runner(mk(small[0]))['pose'].clone()
+    gotLb = runner(mk(large))['pose'].clone()
+    assert torch.equal(got0, got0b) and torch.equal(gotL, gotLb)
+    for g, w in ((got0, want_small[0]), (got1, want_small[1]), (gotL, want_large)):
+        assert float((g - w).abs().max()) <= 5e-5
+
+
+def test_staged_executor_matches_and_reports_stage_times():
+    """stages=True: the four reference `_TIMEIT` stages as four graphs; same results, stage times add up."""
+    from regtr_b200.config import get_config
+    from regtr_b200.regtr import GraphedRegTR, RegTR
+    from regtr_b200.synthetic import make_3dmatch_pair
+    from regtr_b200.weights import random_state_dict
+    cfg = get_config('3dmatch')
+    model = RegTR(cfg).to(DEV).eval()
+    model.load_state_dict(random_state_dict(cfg, 13), strict=True)
+    p = make_3dmatch_pair(2700, 6000)
+    mk = lambda: {'src_xyz': [G(p['src_xyz'])], 'tgt_xyz': [G(p['tgt_xyz'])]}
+    one, four = GraphedRegTR(model, bucket=16384), GraphedRegTR(model, bucket=16384, stages=True)
+    a = one(mk())
+    b = four(mk())
+    b = four(mk())
+    assert torch.equal(a['pose'], b['pose'])
+    ms = four.stage_ms()
+    assert list(ms) == ['preprocess', 'encoder', 'attention_decoder', 'pose'] and all(v > 0 for v in ms.values())

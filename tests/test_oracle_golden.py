@@ -131,3 +131,25 @@ def test_c_preprocess_vs_numpy_twin_randomised():
             assert np.all(np.diff(np.where(valid, a, n + 1).astype(np.int64), axis=1)[valid[:, 1:]] > 0)  # ascending ids
 
     run()
+
+
+# ---- the reference's own sample clouds (real 3DMatch fragments on a 6 mm lattice, ModelNet demo plys) ----------
+
+@pytest.mark.parametrize('case', ['real_3dmatch_redkitchen_0_5', 'real_3dmatch_sun3d_home_38_41'])
+def test_oracle_pyramid_on_real_3dmatch_clouds(case):
+    """The C restatement of the two un-vendored ops on the inputs src/demo.py runs: level sizes, barycentres
+    and every neighbour index equal what the unmodified reference produced (voxel-boundary hits
+    are common on this lattice, 10088 vs 9977 level-1 points depending on the division rule)."""
+    from conftest import check_real_pyramid_against_golden, make_real_case
+    cfg, _, src, tgt = make_real_case(case)
+    meta = pre.preprocess(cfg, [src, tgt])
+    check_real_pyramid_against_golden(meta, load_golden(case))
+
+
+@pytest.mark.parametrize('case', ['real_modelnet_2', 'real_modelnet_630'])
+def test_oracle_forward_on_real_modelnet_pairs(case):
+    from conftest import check_real_forward_against_golden, make_real_case
+    cfg, sd, src, tgt = make_real_case(case)
+    out = O.forward(sd, cfg, [src], [tgt])
+    check_real_forward_against_golden(out, out['kpconv_meta'], load_golden(case), feat_rtol=2e-5, corr_atol=3e-5,
+                                      logit_atol=5e-5, pose_atol=1e-4)
