@@ -469,6 +469,8 @@ def main():
         pipe.drain()
     barrier()
 
+    host_rec = {}
+
     def run_pipelined(src):
         """K steps with `depth` forwards in flight; returns (elapsed ms on the device, bytes in/out)."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -480,7 +482,13 @@ def main():
             if done is not None:
                 outs.append(done['host_pose'].clone())
         t_cpu = time.perf_counter() - t_cpu
-        log(f'host time in submit/result: {1e3 * t_cpu / K:.3f} ms/step')
+        waited = sum(s.wait_s for s in pipe.slots)
+        for s in pipe.slots:
+            s.wait_s = 0.0
+        host_rec['loop_ms_per_step'] = 1e3 * t_cpu / K                       # wall time of the submit loop
+        host_rec['blocked_on_gpu_ms_per_step'] = 1e3 * waited / K            # of which: waiting in event.synchronize
+        host_rec['host_work_ms_per_step'] = 1e3 * (t_cpu - waited) / K       # Python + CUDA API calls
+        log(f'submit loop {1e3 * t_cpu / K:.3f} ms/step, of which waiting for the GPU {1e3 * waited / K:.3f}')
         outs += [o['host_pose'].clone() for o in pipe.drain()]
         pipe.join()
         if world > 1:                           # the run's poses, gathered over the ranks (288 B / pair)
@@ -586,7 +594,7 @@ def main():
                                      'per-step CUDA events, L2 flush between steps not timed'),
             e2e=dict(value=pairs / (t_e2e_ms * 1e-3), unit='pairs/s', h2d_bytes_per_step=h2d,
                      d2h_bytes_per_step=d2h, ms_per_step=t_e2e_ms / K),
-            gpu_launches=launches, clocks=clocks, roofline=roof, rooflines=rooflines, stages=stage_rec,
+            gpu_launches=launches, host=host_rec or None, clocks=clocks, roofline=roof, rooflines=rooflines, stages=stage_rec,
             cpu_baseline=cpu,
             pose_err_vs_oracle=pose_err, impl='b200')
         print(json.dumps(line), flush=True)

@@ -134,6 +134,13 @@ int regtr_instnorm_act(const float* x, const int32_t* offs, int n_clouds, int n_
                        const float* res, float slope, float* out, uint8_t* rowflag_out,
                        void* ws, size_t ws_bytes, int32_t* counters, void* stream);
 
+/* The apply pass alone: out = act((x - mean) * rstd + res) with stats (n_clouds, C, 2) = (mean, rstd) produced
+ * elsewhere -- by regtr_gemm_tf32x3_instats, which accumulates them in the GEMM epilogue so that the Linear ->
+ * InstanceNorm pairs of the KPConv blocks (kpconv_blocks.py:546-561, 401-406 + 497-519) never re-read their
+ * output for the statistics.  rowflag_out as in regtr_instnorm_act. */
+int regtr_instnorm_apply(const float* x, const int32_t* offs, int n_clouds, int n_cap, int C, const float* stats,
+                         const float* res, float slope, float* out, uint8_t* rowflag_out, void* stream);
+
 /* ---- dense layers ---------------------------------------------------------------- */
 
 /* x = hi + lo with both halves exactly representable in TF32 (low 13 mantissa bits zero);
@@ -153,6 +160,18 @@ int regtr_gemm_tf32x3(const float* A, int lda, const float* B_hi, const float* B
                       float* C, int ldc, const float* bias, const float* R, int ldr,
                       int M, int N, int K, const int32_t* m_dev, int relu,
                       void* ws, size_t ws_bytes, void* stream);
+
+/* C = A @ B^T (no bias / residual / activation) PLUS the per-cloud InstanceNorm statistics of C:
+ * stats (n_clouds, N, 2) = (mean, 1/sqrt(biased var + eps)) over the rows [offs[c], offs[c+1]) of each column.
+ * Every epilogue warp reduces its 32 rows in a fixed shuffle tree and adds to 128-bit fixed-point accumulators
+ * with 64-bit INTEGER atomics (associative: run-to-run bit-identical statistics); the launch's last CTA
+ * finalises.  N % 32 == 0.  acc: regtr_instnorm_acc_bytes(n_clouds, N) bytes, 256-byte aligned, ZERO before the
+ * first call and owned by this op between calls (every call leaves it zero). */
+size_t regtr_instnorm_acc_bytes(int n_clouds, int C);
+int regtr_gemm_tf32x3_instats(const float* A, int lda, const float* B_hi, const float* B_lo, int ldb,
+                              float* C, int ldc, int M, int N, int K, const int32_t* m_dev,
+                              const int32_t* offs, int n_clouds, float eps, void* acc, float* stats,
+                              void* ws, size_t ws_bytes, void* stream);
 
 /* ---- transformer ------------------------------------------------------------------ */
 

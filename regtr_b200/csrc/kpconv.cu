@@ -5,6 +5,7 @@
 // Reference behaviour replaced (paths relative to /root/reference/src):
 //   models/backbone_kpconv/kpconv_blocks.py:269-414  KPConv.forward (rigid, linear, sum)
 //   models/backbone_kpconv/kpconv_blocks.py:127-143  max_pool
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -346,6 +347,178 @@ k_kpconv_agg_mma(const float* __restrict__ q, const float* __restrict__ s, const
     }
 }
 
+// ---- software-pipelined persistent variant (the default for Cin % 32 == 0, K <= 64) -------------------------
+// k_kpconv_agg_mma above runs one query per warp start to finish: index row -> support coordinates -> feature
+// rows are three DEPENDENT global round trips (~2000 cycles) in front of ~800 issue slots of work, and the
+// profile showed the SM idle 47 % of the time waiting on them (long-scoreboard 3.7 warps per issue).  Here
+// every warp is persistent and walks a strided list of work items (query, 32-channel slice) with the chain
+// pipelined ACROSS items: while item i runs on the tensor cores, the feature rows of item i+1 are in flight
+// (cp.async into the other half of a double buffer), the coordinates of item i+2 are being loaded into
+// registers and the index row of item i+3 has been requested.  Same fragment construction, same arithmetic
+// and the same output as k_kpconv_agg_mma<1>.
+constexpr int PIPE_WARPS = 4;
+
+struct AggItem {            // registers that travel with an item through the load stages
+    int id0, id1;           // neighbour ids of lanes (lane, lane + 32) of the index row
+    float x0, y0, z0, x1, y1, z1;
+    float qx, qy, qz;
+    int f0, f1;             // "row sums to > 0" flags of the two neighbours
+};
+
+__global__ void __launch_bounds__(PIPE_WARPS * 32, 4)
+k_kpconv_agg_pipe(const float* __restrict__ q, const float* __restrict__ s, const int32_t* __restrict__ idx,
+                  const float* __restrict__ x, const uint8_t* __restrict__ flags, const float* __restrict__ kp,
+                  int Nq, int Ns, const int32_t* __restrict__ nq_dev, const int32_t* __restrict__ ns_dev, int K, int Cin,
+                  int log2_slices, float inv_extent, float* __restrict__ wf) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Kp = (K + 7) & ~7;
+    constexpr int ROW = 32;
+    // per warp, two buffers of: rows[Kp][32] (16-byte chunks swizzled) | rel[Kp] (float4) | id[Kp]
+    const int buf_floats = Kp * (ROW + 5);
+    float* wbase = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 2 * buf_floats;
+    if (ns_dev) Ns = min(Ns, *ns_dev);
+    const int nq_real = nq_dev ? min(Nq, *nq_dev) : Nq;
+    const int W = gridDim.x * PIPE_WARPS, w = blockIdx.x * PIPE_WARPS + warp;
+    const int g = lane >> 2, t = lane & 3;
+    // capacity padding rows: zero the band up to the next multiple of 128 (the consumer GEMM's last tile)
+    if (nq_dev) {
+        const int band_end = min(pad_band_end(nq_real), Nq);
+        for (int r = nq_real + w; r < band_end; r += W) {
+            float4* o = reinterpret_cast<float4*>(wf + (size_t)r * (KP * Cin));
+            for (int i = lane; i < KP * Cin / 4; i += 32) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    const long long n_items = (long long)nq_real << log2_slices;
+    const int slice_mask = (1 << log2_slices) - 1;
+
+    const float ax = __ldg(kp + 3 * g), ay = __ldg(kp + 3 * g + 1), az = __ldg(kp + 3 * g + 2);
+    const bool row_b = g + 8 < KP;                // M = 16 rows, kernel points 0..14; row 15: far away -> 0
+    const float bx = row_b ? __ldg(kp + 3 * g + 24) : -1e6f, by = row_b ? __ldg(kp + 3 * g + 25) : -1e6f,
+                bz = row_b ? __ldg(kp + 3 * g + 26) : -1e6f;
+
+    // ---- stage A: request the index row of item `it`
+    auto stage_idx = [&](long long it, AggItem& a) {
+        a.id0 = Ns; a.id1 = Ns;
+        if (it < n_items) {
+            const int32_t* row = idx + (size_t)(it >> log2_slices) * K;
+            if (lane < K) a.id0 = __ldg(row + lane);
+            if (lane + 32 < K) a.id1 = __ldg(row + lane + 32);
+        }
+    };
+    // ---- stage B: request the support coordinates / flags of the item's neighbours and its query point
+    auto stage_coords = [&](long long it, AggItem& a) {
+        const bool v0 = a.id0 >= 0 && a.id0 < Ns, v1 = a.id1 >= 0 && a.id1 < Ns;
+        a.x0 = a.y0 = a.z0 = a.x1 = a.y1 = a.z1 = 0.f; a.f0 = a.f1 = 0;
+        if (v0) { a.x0 = __ldg(s + 3 * a.id0); a.y0 = __ldg(s + 3 * a.id0 + 1); a.z0 = __ldg(s + 3 * a.id0 + 2); a.f0 = flags[a.id0]; }
+        if (v1) { a.x1 = __ldg(s + 3 * a.id1); a.y1 = __ldg(s + 3 * a.id1 + 1); a.z1 = __ldg(s + 3 * a.id1 + 2); a.f1 = flags[a.id1]; }
+        if (!v0) a.id0 = -1;
+        if (!v1) a.id1 = -1;
+        a.qx = a.qy = a.qz = 0.f;
+        if (it < n_items) {
+            const int qi = (int)(it >> log2_slices);
+            a.qx = __ldg(q + 3 * qi); a.qy = __ldg(q + 3 * qi + 1); a.qz = __ldg(q + 3 * qi + 2);
+        }
+    };
+    // ---- stage C: compact the valid neighbours into buffer `b`, start the cp.async of their feature rows.
+    // Returns (padded neighbour count, counted neighbours) of the item.
+    auto stage_rows = [&](long long it, const AggItem& a, int b, int& padded, int& counted) {
+        float* rows_s = wbase + b * buf_floats;
+        float4* rel_s = reinterpret_cast<float4*>(rows_s + Kp * ROW);
+        int* id_s = reinterpret_cast<int*>(rows_s + Kp * (ROW + 4));
+        const bool v0 = a.id0 >= 0, v1 = a.id1 >= 0;
+        const unsigned m0 = __ballot_sync(0xffffffffu, v0), m1 = __ballot_sync(0xffffffffu, v1);
+        const unsigned lt = (1u << lane) - 1u;
+        const int n0 = __popc(m0);
+        if (v0) { const int p = __popc(m0 & lt); rel_s[p] = make_float4(a.x0 - a.qx, a.y0 - a.qy, a.z0 - a.qz, 0.f); id_s[p] = a.id0; }
+        if (v1) { const int p = n0 + __popc(m1 & lt); rel_s[p] = make_float4(a.x1 - a.qx, a.y1 - a.qy, a.z1 - a.qz, 0.f); id_s[p] = a.id1; }
+        const int base = n0 + __popc(m1);
+        counted = __popc(__ballot_sync(0xffffffffu, v0 && a.f0)) + __popc(__ballot_sync(0xffffffffu, v1 && a.f1));
+        // pad to a whole k-step: a loadable row (row 0 exists whenever there is a valid neighbour) and a far-away
+        // position, i.e. an influence of exactly 0
+        padded = (base + 7) & ~7;
+        if (lane < padded - base) { id_s[base + lane] = 0; rel_s[base + lane] = make_float4(1e6f, 1e6f, 1e6f, 0.f); }
+        __syncwarp();
+        if (it < n_items) {
+            const int c = lane & 7, rg = lane >> 3;                  // 8 16-byte chunks per row, 4 rows per instruction
+            const float* xs = x + (size_t)((int)it & slice_mask) * 32 + 4 * c;
+            uint32_t dst = (uint32_t)__cvta_generic_to_shared(rows_s) + (uint32_t)(rg * ROW) * 4u;
+            for (int n = rg; n < padded; n += 4, dst += 4 * ROW * 4) {
+                const float* src = xs + (size_t)id_s[n] * Cin;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(((c + 2 * n) & 7) * 16)), "l"(src) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // ---- prologue: fill the pipeline
+    AggItem a1, a2;                          // a1: item i+1 (coordinates requested), a2: item i+2 (index row requested)
+    int pad_cur = 0, cnt_cur = 0, pad_nxt = 0, cnt_nxt = 0;
+    long long it = w;
+    {
+        AggItem a0;
+        stage_idx(it, a0); stage_idx(it + W, a1); stage_idx(it + 2LL * W, a2);
+        stage_coords(it, a0); stage_coords(it + W, a1);
+        stage_rows(it, a0, 0, pad_cur, cnt_cur);
+    }
+    int b = 0;
+    for (; it < n_items; it += W, b ^= 1) {
+        // rows of item i+1 (coordinates arrived during the previous item), coordinates of i+2, index row of i+3
+        stage_rows(it + W, a1, b ^ 1, pad_nxt, cnt_nxt);
+        a1 = a2;
+        stage_coords(it + 2LL * W, a1);
+        stage_idx(it + 3LL * W, a2);
+
+        // ---- item i on the tensor cores (rows landed: only the newest cp.async group may still be in flight)
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        const float* rows_s = wbase + b * buf_floats;
+        const float4* rel_s = reinterpret_cast<const float4*>(rows_s + Kp * ROW);
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+        for (int k0 = 0; k0 < pad_cur; k0 += 8) {
+            const int n0 = k0 + t, n1 = n0 + 4;        // n0 & 3 == n1 & 3 == t
+            const float4 v0 = *reinterpret_cast<const float4*>(rows_s + n0 * ROW + 4 * ((g + 2 * t) & 7));
+            const float4 v1 = *reinterpret_cast<const float4*>(rows_s + n1 * ROW + 4 * ((g + 2 * t) & 7));
+            const float4 r0 = rel_s[n0], r1 = rel_s[n1];
+            const float hw[4] = {influence(r0, ax, ay, az, inv_extent), influence(r0, bx, by, bz, inv_extent),
+                                 influence(r1, ax, ay, az, inv_extent), influence(r1, bx, by, bz, inv_extent)};
+            uint32_t a_hi[4], a_lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { a_hi[e] = tf32_head(hw[e]); a_lo[e] = __float_as_uint(hw[e] - __uint_as_float(a_hi[e])); }
+            const float b0f[4] = {v0.x, v0.y, v0.z, v0.w};
+            const float b1f[4] = {v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t h0 = tf32_head(b0f[j]), h1 = tf32_head(b1f[j]);
+                const uint32_t l0 = __float_as_uint(b0f[j] - __uint_as_float(h0));
+                const uint32_t l1 = __float_as_uint(b1f[j] - __uint_as_float(h1));
+                mma_tf32_16x8x8(acc[j], a_lo, h0, h1);
+                mma_tf32_16x8x8(acc[j], a_hi, l0, l1);
+                mma_tf32_16x8x8(acc[j], a_hi, h0, h1);
+            }
+        }
+        float inv;                                    // 1 / max(count, 1): one MUFU (<= 1 ulp)
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"((float)max(cnt_cur, 1)));
+        {
+            float* o = wf + (size_t)(it >> log2_slices) * (KP * Cin) + ((int)it & slice_mask) * 32 + g * Cin + 8 * t;
+            reinterpret_cast<float4*>(o)[0] = make_float4(acc[0][0] * inv, acc[1][0] * inv, acc[2][0] * inv, acc[3][0] * inv);
+            reinterpret_cast<float4*>(o)[1] = make_float4(acc[0][1] * inv, acc[1][1] * inv, acc[2][1] * inv, acc[3][1] * inv);
+            if (row_b) {
+                float* o2 = o + 8 * Cin;
+                reinterpret_cast<float4*>(o2)[0] = make_float4(acc[0][2] * inv, acc[1][2] * inv, acc[2][2] * inv, acc[3][2] * inv);
+                reinterpret_cast<float4*>(o2)[1] = make_float4(acc[0][3] * inv, acc[1][3] * inv, acc[2][3] * inv, acc[3][3] * inv);
+            }
+        }
+        __syncwarp();                                 // all lanes are done with buffer b before it is refilled
+        pad_cur = pad_nxt; cnt_cur = cnt_nxt;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 // Cin = 1 (the first block: a constant-1 input feature).  Per query the whole op is
 //   wf[p] = sum_k h(rel_k - kp_p) * x[id_k] / #{k : x[id_k] > 0}       (15 numbers)
 // and, FUSEd, out[c] = sum_p wf[p] W[p, c].  Lane (p = lane & 15, half = lane >> 4) sums its kernel point over
@@ -626,6 +799,29 @@ int regtr_kpconv_aggregate(const float* q, const float* s, const int32_t* idx, c
                                                                                    Ns, nq_dev, ns_dev, K, Cin, extent, wf);
         REGTR_CHECK_LAUNCH();
         return REGTR_OK;
+    }
+    {   // default: software-pipelined persistent kernel (REGTR_AGG_IMPL=mma / ffma select the older kernels for A/B)
+        const char* e = getenv("REGTR_AGG_IMPL");
+        const int S = Cin / 32;
+        if (!e && K <= 64 && (S & (S - 1)) == 0) {
+            const int Kp = (K + 7) & ~7;
+            const size_t smem = (size_t)PIPE_WARPS * 2 * Kp * (32 + 5) * sizeof(float);
+            static size_t attr_smem = 0;
+            if (smem > 48 * 1024 && smem > attr_smem) {
+                if (cudaFuncSetAttribute(k_kpconv_agg_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                    return REGTR_ERR_UNSUPPORTED;
+                attr_smem = smem;
+            }
+            int log2s = 0;
+            while ((1 << log2s) < S) ++log2s;
+            const long long items = (long long)Nq * S;
+            const int per_sm = smem <= 56 * 1024 ? 4 : (smem <= 75 * 1024 ? 3 : 2);
+            const int grid = (int)std::min<long long>((long long)REGTR_NUM_SMS * per_sm, (items + PIPE_WARPS - 1) / PIPE_WARPS);
+            k_kpconv_agg_pipe<<<grid, PIPE_WARPS * 32, smem, st>>>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, Cin,
+                                                                  log2s, 1.f / extent, wf);
+            REGTR_CHECK_LAUNCH();
+            return REGTR_OK;
+        }
     }
     if (agg_use_mma()) {
         int rc = REGTR_ERR_UNSUPPORTED;

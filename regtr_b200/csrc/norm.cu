@@ -275,6 +275,28 @@ int regtr_instnorm_act(const float* x, const int32_t* offs, int n_clouds, int n_
     return REGTR_OK;
 }
 
+// Apply pass alone, with statistics produced elsewhere (the GEMM epilogue, regtr_gemm_tf32x3_instats).
+int regtr_instnorm_apply(const float* x, const int32_t* offs, int n_clouds, int n_cap, int C, const float* stats,
+                         const float* res, float slope, float* out, uint8_t* rowflag_out, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (!offs || n_clouds <= 0 || n_cap < 0 || C <= 0) return REGTR_ERR_ARG;
+    if (C % 4 != 0) return REGTR_ERR_UNSUPPORTED;
+    if (n_cap == 0) return REGTR_OK;
+    if (!x || !out || !stats) return REGTR_ERR_ARG;
+    const float2* stp = reinterpret_cast<const float2*>(stats);
+    if (rowflag_out) {
+        const int c4n = C / 4;
+        if (c4n > 32 || (c4n & (c4n - 1))) return REGTR_ERR_UNSUPPORTED;   // the row must sit inside one warp
+        k_in_apply<true><<<regtr_cdiv((long long)n_cap * c4n, 256), 256, 0, st>>>(x, offs, n_clouds, n_cap, C, stp, res, slope,
+                                                                                  out, rowflag_out);
+    } else {
+        k_in_apply<false><<<regtr_cdiv((long long)n_cap * (C / 4), 256), 256, 0, st>>>(x, offs, n_clouds, n_cap, C, stp, res,
+                                                                                      slope, out, nullptr);
+    }
+    REGTR_CHECK_LAUNCH();
+    return REGTR_OK;
+}
+
 int regtr_layernorm_pos(const float* x, const float* gamma, const float* beta, const float* pos, int n,
                         const int32_t* n_dev, int E, float eps, float* y, float* y_pos, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;

@@ -60,12 +60,12 @@ class Pyramid:
         """`upsamples[li]` (kpconv.py:503-507): for every point of level li its first-K neighbours of level
         li+1 inside radius 2 r_li, int64, capacity-shaped.  Computed on demand from the retained cell lists:
         RegTR.forward never reads it."""
-        if self.up64[li] is None and self.levels[li]['strided']:
-            lvl = self.levels[li]
-            _, self.up64[li] = ops.ball_query(self.points[li], self.offs_all[li], self.points[li + 1],
-                                              self.offs_all[li + 1], self.grids[li + 1], lvl['K'], 2 * lvl['radius'],
-                                              q_order=self.grids[li].order, want32=False)
-        return self.up64[li]
+        if self.up64[li] is not None or not self.levels[li]['strided']:
+            return self.up64[li]
+        lvl = self.levels[li]           # NOT cached here: a graph-owned pyramid is refilled by every replay
+        return ops.ball_query(self.points[li], self.offs_all[li], self.points[li + 1], self.offs_all[li + 1],
+                              self.grids[li + 1], lvl['K'], 2 * lvl['radius'], q_order=self.grids[li].order,
+                              want32=False)[1]
 
     def n_dev(self, level):
         """1-element int32 device view holding the number of points of `level`."""
@@ -252,11 +252,13 @@ class KPConv(nn.Module):
         self.kernel_points = nn.Parameter(torch.from_numpy(kernel_disposition(radius, kernel_size)),
                                           requires_grad=False)
 
-    def forward(self, q_pts, s_pts, neighb_inds, x, nq_dev=None, ns_dev=None, row_flags=None):
+    def forward(self, q_pts, s_pts, neighb_inds, x, nq_dev=None, ns_dev=None, row_flags=None, instats=None):
+        """instats=(offs, n_clouds): also return the per-cloud InstanceNorm statistics of the output, accumulated
+        in the contraction GEMM's epilogue -> (out, stats)."""
         idx = neighb_inds if neighb_inds.dtype == torch.int32 else neighb_inds.to(torch.int32)
         return ops.kpconv(q_pts.contiguous(), s_pts.contiguous(), idx.contiguous(), x.contiguous(),
                           self.weights, self.kernel_points, self.KP_extent, nq_dev=nq_dev, ns_dev=ns_dev,
-                          row_flags=row_flags)
+                          row_flags=row_flags, instats=instats)
 
     def __repr__(self):
         return 'KPConv(radius: {:.2f}, extent: {:.2f}, in_feat: {:d}, out_feat: {:d})'.format(
@@ -283,6 +285,10 @@ class BatchNormBlock(nn.Module):
             y = y + res
         return F.leaky_relu(y, slope) if slope >= 0 else y
 
+    def apply(self, x, stats, offs, n_clouds, res=None, slope=-1.0, want_flags=False):
+        """Normalise with statistics that the producing GEMM accumulated in its epilogue."""
+        return ops.instnorm_apply(x, offs, n_clouds, stats, res=res, slope=slope, want_flags=want_flags)
+
     def forward(self, x, stack_lengths):
         offs = ops.make_offsets(stack_lengths, x.device)
         return self.fuse(x.contiguous(), offs, offs.numel() - 1)
@@ -299,6 +305,10 @@ class UnaryBlock(nn.Module):
 
     def fuse(self, x, offs, n_clouds, res=None, final_slope=None, m_dev=None, want_flags=False):
         slope = final_slope if final_slope is not None else (-1.0 if self.no_relu else 0.1)
+        if self.use_bn and self.out_dim % 32 == 0:
+            # Linear with the InstanceNorm statistics accumulated in the GEMM epilogue, then the apply pass
+            y, stats = ops.linear_instats(x, self.mlp.weight, offs, n_clouds, m_dev=m_dev)
+            return self.batch_norm.apply(y, stats, offs, n_clouds, res=res, slope=slope, want_flags=want_flags)
         return self.batch_norm.fuse(ops.linear(x, self.mlp.weight, m_dev=m_dev), offs, n_clouds, res=res,
                                     slope=slope, want_flags=want_flags)
 
@@ -370,8 +380,12 @@ class ResnetBottleneckBlock(nn.Module):
         else:
             x = self.unary1.fuse(features, offs_pre, nc, m_dev=ns_dev) if isinstance(self.unary1, UnaryBlock) \
                 else features
-        x = self.KPConv(q, s, idx, x, nq_dev, ns_dev, row_flags=flags)
-        x = self.batch_norm_conv.fuse(x, offs_post, nc, slope=0.1)
+        if self.use_bn and self.KPConv.out_channels % 32 == 0:
+            x, stats = self.KPConv(q, s, idx, x, nq_dev, ns_dev, row_flags=flags, instats=(offs_post, nc))
+            x = self.batch_norm_conv.apply(x, stats, offs_post, nc, slope=0.1)
+        else:
+            x = self.KPConv(q, s, idx, x, nq_dev, ns_dev, row_flags=flags)
+            x = self.batch_norm_conv.fuse(x, offs_post, nc, slope=0.1)
         shortcut = ops.max_pool(features, idx, ns_dev) if 'strided' in self.block_name else features
         if isinstance(self.unary_shortcut, UnaryBlock):
             shortcut = self.unary_shortcut.fuse(shortcut, offs_post, nc, m_dev=nq_dev)

@@ -45,6 +45,9 @@ SIGNATURES = {
     'regtr_instnorm_ws_bytes': (_Z, [_I, _I, _I]),
     'regtr_instnorm_counter_bytes': (_Z, [_I, _I]),
     'regtr_instnorm_act': (_I, [_P, _P, _I, _I, _I, _F, _P, _F, _P, _P, _P, _Z, _P, _P]),
+    'regtr_instnorm_apply': (_I, [_P, _P, _I, _I, _I, _P, _P, _F, _P, _P, _P]),
+    'regtr_instnorm_acc_bytes': (_Z, [_I, _I]),
+    'regtr_gemm_tf32x3_instats': (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _F, _P, _P, _P, _Z, _P]),
     'regtr_split_tf32': (_I, [_P, _c.c_longlong, _P, _P, _P]),
     'regtr_gemm_ws_bytes': (_Z, [_I, _I, _I]),
     'regtr_gemm_tf32x3': (_I, [_P, _I, _P, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P, _Z, _P]),

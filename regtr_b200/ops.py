@@ -178,7 +178,7 @@ def ball_query(q, q_offs, s, s_offs, grid: CellGrid, K: int, radius: float, q_or
 # ------------------------------------------------------------------------ encoder
 
 def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=None, nq_dev=None, ns_dev=None,
-           row_flags=None):
+           row_flags=None, instats=None):
     """KPConv.forward (rigid / linear / sum).  idx32 (Nq,K) int32, x (Ns,Cin) -> (Nq,Cout).
     nq_dev / ns_dev: optional 1-element int32 device tensors with the actual counts when the
     leading dimensions are capacities."""
@@ -192,6 +192,9 @@ def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=No
     if P != 15 or kernel_points.shape != (15, 3) or Cin_w != Cin or q_pts.shape[0] != Nq or s_pts.shape[0] != Ns:
         raise ValueError('kpconv: inconsistent shapes')
     out = torch.empty((Nq, Cout), dtype=torch.float32, device=x.device) if out is None else out
+    stats = None
+    if instats is not None and (Cin == 1 or Cout % 32):
+        raise ValueError('kpconv: the statistics epilogue needs Cin > 1 and Cout % 32 == 0')
     nb = L.regtr_kpconv_fwd_ws_bytes(Nq, Ns, Cin, Cout) if Cin == 1 else L.regtr_kpconv_ws_bytes(Nq, Ns, Cin)
     ws = workspace(nb, x.device, 'kpconv')
     trace = KPCONV_TRACE
@@ -218,14 +221,17 @@ def kpconv(q_pts, s_pts, idx32, x, weights, kernel_points, extent: float, out=No
         if ev:
             ev[1].record()
             ev.append(True)
-        gemm(wf, hi, lo, m_dev=nq_dev, out=out)
+        if instats is not None:                 # (offs, n_clouds): statistics of the output in the GEMM epilogue
+            out, stats = gemm_instats(wf, hi, lo, instats[0], instats[1], m_dev=nq_dev, out=out)
+        else:
+            gemm(wf, hi, lo, m_dev=nq_dev, out=out)
     if ev:
         ev[2].record()
         trace.append((ev[0], ev[2], dict(Nq=Nq, Ns=Ns, K=K, Cin=Cin, Cout=Cout, idx=idx32,
                                          mid=ev[1] if len(ev) > 3 else None,
                                          args=(q_pts, s_pts, idx32, x, kernel_points, float(extent)),
                                          row_flags=row_flags)))
-    return out
+    return out if instats is None else (out, stats)
 
 
 def kpconv_aggregate(q_pts, s_pts, idx32, x, kernel_points, extent: float, wf=None, nq_dev=None, ns_dev=None,
@@ -277,6 +283,22 @@ def instnorm_act(x, offs, n_clouds: int, res=None, slope: float = -1.0, eps: flo
     return (out, flags) if want_flags else out
 
 
+def instnorm_apply(x, offs, n_clouds: int, stats, res=None, slope: float = -1.0, out=None, want_flags: bool = False):
+    """Apply pass of the per-cloud InstanceNorm with statistics from `gemm_instats`:
+    out = act((x - mean) * rstd + res)."""
+    L = _lib.load()
+    _chk(x, torch.float32, 'x', 2); _chk(offs, torch.int32, 'offs', 1); _chk(stats, torch.float32, 'stats', 3)
+    n, C = x.shape
+    out = torch.empty_like(x) if out is None else out
+    flags = None
+    if want_flags and C // 4 <= 32 and (C // 4) & (C // 4 - 1) == 0:
+        flags = torch.empty(max(n, 1), dtype=torch.uint8, device=x.device)
+    _lib.check(L.regtr_instnorm_apply(_p(x), _p(offs), n_clouds, n, C, _p(stats), _p(res), float(slope), _p(out),
+                                      _p(flags), _stream()), 'regtr_instnorm_apply')
+    _count(1)
+    return (out, flags) if want_flags else out
+
+
 # -------------------------------------------------------------------- dense layers
 
 def split_weight(w: torch.Tensor, transpose: bool = False):
@@ -319,6 +341,37 @@ def gemm(a, b_hi, b_lo, bias=None, residual=None, relu=False, m_dev=None, out=No
                'regtr_gemm_tf32x3')
     _count(2 if nb > 256 else 1)
     return out
+
+
+def gemm_instats(a, b_hi, b_lo, offs, n_clouds: int, eps: float = 1e-5, m_dev=None, out=None):
+    """a @ B^T plus the per-cloud InstanceNorm statistics of the result, accumulated in the GEMM epilogue
+    (deterministic fixed-point integer atomics).  -> (out (M,N), stats (n_clouds, N, 2) = (mean, rstd))."""
+    L = _lib.load()
+    if not a.is_cuda or a.dtype != torch.float32 or a.dim() != 2 or a.stride(1) != 1:
+        raise ValueError('gemm: A must be a CUDA fp32 matrix with unit column stride')
+    M, K = a.shape
+    N = b_hi.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device) if out is None else out
+    stats = torch.empty((n_clouds, N, 2), dtype=torch.float32, device=a.device)
+    nb = L.regtr_gemm_ws_bytes(M, N, K)
+    ws = workspace(nb, a.device, 'gemm')
+    acc = workspace(L.regtr_instnorm_acc_bytes(n_clouds, N), a.device, 'instnorm_acc', zero=True)
+    if TRACE is not None:
+        TRACE.append(('gemm', dict(M=M, N=N, K=K, split_k=nb > 256, instats=True),
+                      lambda: gemm_instats(a, b_hi, b_lo, offs, n_clouds, eps, m_dev=m_dev, out=out)))
+    _lib.check(L.regtr_gemm_tf32x3_instats(_p(a), a.stride(0), _p(b_hi), _p(b_lo), b_hi.stride(0), _p(out), out.stride(0),
+                                           M, N, K, _p(m_dev), _p(offs), n_clouds, float(eps), _p(acc), _p(stats),
+                                           _p(ws), ws.numel(), _stream()), 'regtr_gemm_tf32x3_instats')
+    _count(2 if nb > 256 else 1)
+    return out, stats
+
+
+def linear_instats(x, weight, offs, n_clouds: int, eps: float = 1e-5, m_dev=None):
+    """nn.Linear(bias=False) followed by InstanceNorm statistics (UnaryBlock, kpconv_blocks.py:546-561)."""
+    if x.shape[1] % 4 or x.stride(0) % 4 or x.data_ptr() % 16:
+        raise _lib.RegtrLibError(f'linear: K={x.shape[1]}: rows must be 16-byte aligned multiples of 4 floats')
+    hi, lo = split_weight(weight)
+    return gemm_instats(x, hi, lo, offs, n_clouds, eps, m_dev=m_dev)
 
 
 def linear(x, weight, bias=None, residual=None, relu=False, m_dev=None):
@@ -412,8 +465,8 @@ def mha_varlen(q, k, v, q_start, q_len, k_start, k_len, max_q_len: int, n_heads:
             raise ValueError(f'mha_varlen: {nm} must be a CUDA fp32 matrix with unit column stride')
     E = q.shape[1]
     dh = E // n_heads
-    # zeros: rows outside every problem (capacity padding) stay finite for the GEMMs downstream
-    out = torch.zeros((q.shape[0], E), dtype=torch.float32, device=q.device) if out is None else out
+    # rows outside every problem (capacity padding) stay uninitialised: every consumer is row-wise and skips them
+    out = torch.empty((q.shape[0], E), dtype=torch.float32, device=q.device) if out is None else out
     if TRACE is not None:
         ql, kl = q_len.tolist(), k_len.tolist()
         TRACE.append(('mha', dict(pairs_qk=sum(a * b for a, b in zip(ql, kl)), E=E, tokens=sum(ql)),

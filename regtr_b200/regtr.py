@@ -19,6 +19,7 @@ Training (`compute_loss`, autograd through the custom kernels) is a "next" row.
 from __future__ import annotations
 
 import logging
+import time
 import weakref
 
 import torch
@@ -233,6 +234,7 @@ class GraphedRegTR:
         self.ratios = {}
         self.graphs = {}
         self.fallbacks = 0
+        self.wait_s = 0.0               # host time spent blocked in result() waiting for the GPU (diagnostics)
         weakref.finalize(self, GraphedRegTR._release_all, self.graphs)
 
     @staticmethod
@@ -379,7 +381,9 @@ class GraphedRegTR:
         static buffers: valid until the next submit on the same capacity bucket)."""
         key, st, batch, B = ticket
         model = self.model
+        t0 = time.perf_counter()
         st['done'].synchronize()
+        self.wait_s += time.perf_counter() - t0
         pyr = st['pyr']
         n_lvl = len(pyr.levels)
         n_meta = st['n_meta']

@@ -41,7 +41,9 @@ print('m_dev: err', e, 'untouched rows', bool((out[300:] == 7.0).all()))
 ok &= e < 1e-4 and bool((out[300:] == 7.0).all())
 # timing
 import time
-for (M, N, K) in [(38061, 128, 64), (38061, 32, 480), (9977, 64, 960), (749, 256, 3840), (750, 768, 256)]:
+for (M, N, K) in [(38061, 128, 64), (38061, 32, 64), (38061, 32, 480), (38061, 128, 32), (9977, 64, 960), (9977, 256, 64),
+                  (2741, 128, 1920), (749, 256, 3840), (750, 768, 256), (750, 256, 1024), (6000, 768, 256), (6000, 1024, 256),
+                  (6000, 256, 1024), (304000, 32, 480), (80000, 64, 960)]:
     a = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev)
     hi, lo = ops.split_weight(w)
     for _ in range(3): ops.gemm(a, hi, lo); (a @ w.t())

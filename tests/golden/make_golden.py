@@ -132,6 +132,39 @@ def real_fixture(name):
           'pose[-1]', fx['pose'][-1, 0, 0])
 
 
+def benchmark_fixture():
+    """Category-b fixtures for the end-to-end benchmark test (SURVEY.md 8f N1 + N2): the `gt.log` / `gt.info`
+    entries (src/datasets/3dmatch/benchmarks/3DMatch/<scene>/) and the `test_3DMatch_info.pkl` rows
+    (src/datasets/3dmatch/) of the two shipped sample pairs that belong to the 3DMatch benchmark."""
+    import json
+    import pickle
+    ref = '/root/reference/src/datasets/3dmatch'
+    info = pickle.load(open(os.path.join(ref, 'test_3DMatch_info.pkl'), 'rb'))
+    want = {('7-scenes-redkitchen', 5, 0): 'real_3dmatch_redkitchen_0_5',
+            ('sun3d-hotel_umd-maryland_hotel3', 15, 8): 'real_3dmatch_sun3d_hotel3_8_15'}
+    rows = []
+    for i, (sp, tp) in enumerate(zip(info['src'], info['tgt'])):
+        scene = sp.split('/')[1]
+        key = (scene, int(sp.split('_')[-1][:-4]), int(tp.split('_')[-1][:-4]))
+        if key in want:
+            rows.append(dict(src=sp, tgt=tp, rot=np.asarray(info['rot'][i]).tolist(), trans=np.asarray(info['trans'][i]).tolist(),
+                             overlap=float(info['overlap'][i]), fixture=want[key]))
+    out_dir = os.path.join(OUT, 'real', 'benchmarks', '3DMatch')
+    for scene, si, ti in want:
+        os.makedirs(os.path.join(out_dir, scene), exist_ok=True)
+        for fname, n_rows in (('gt.log', 4), ('gt.info', 6)):
+            lines = open(os.path.join(ref, 'benchmarks', '3DMatch', scene, fname)).read().split('\n')
+            for k, ln in enumerate(lines):
+                f = ln.split()
+                if len(f) == 3 and int(f[0]) == ti and int(f[1]) == si:
+                    open(os.path.join(out_dir, scene, fname), 'w').write('\n'.join(lines[k:k + 1 + n_rows]) + '\n')
+                    break
+            else:
+                raise RuntimeError((scene, fname))
+    json.dump(rows, open(os.path.join(OUT, 'real', 'test_3DMatch_info_rows.json'), 'w'), indent=1)
+    print('benchmark fixture', [r['src'] for r in rows])
+
+
 def forward_fixture(name):
     cfg_name, wseed, makers, *rest = FORWARD_CASES[name]
     variant = bool(rest)
@@ -333,14 +366,19 @@ if __name__ == '__main__':
     torch.manual_seed(0)
     np.random.seed(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'real':          # only the real-data fixtures (minutes of CPU)
+        benchmark_fixture()
         for case in (sys.argv[2:] or REAL_CASES):
             real_fixture(case)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'bench':
+        benchmark_fixture()
         sys.exit(0)
     eval_fixtures()
     loss_fixture()
     op_fixtures()
     for case in FORWARD_CASES:
         forward_fixture(case)
+    benchmark_fixture()
     for case in REAL_CASES:
         real_fixture(case)
     for f in sorted(os.listdir(OUT)):

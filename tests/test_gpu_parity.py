@@ -41,14 +41,18 @@ def test_kpconv_vs_reference_golden(ops_golden):
     assert np.all(N(y)[3] == 0)
 
 
-@pytest.mark.parametrize('impl', ['mma', 'ffma'])
+@pytest.mark.parametrize('impl', ['pipe', 'mma', 'ffma'])
 @pytest.mark.parametrize('cin,cout', [(1, 64), (4, 16), (32, 32), (64, 64), (128, 128), (256, 256)])
 def test_kpconv_all_channel_paths_vs_oracle(cin, cout, impl, monkeypatch):
-    """Both aggregation implementations (tensor-core mma.sync, the default, and the CUDA-core kernels kept
-    for A/B and as the large-K fallback) on every channel-width path, incl. the fused Cin=1 block."""
+    """The aggregation implementations (software-pipelined persistent tensor-core kernel = the default; the
+    one-query-per-warp tensor-core kernel and the CUDA-core kernels kept for A/B and as the large-K fallback)
+    on every channel-width path, incl. the fused Cin=1 block."""
     from oracle import regtr_oracle as O
     from regtr_b200 import ops
-    monkeypatch.setenv('REGTR_AGG_IMPL', impl)
+    if impl == 'pipe':
+        monkeypatch.delenv('REGTR_AGG_IMPL', raising=False)
+    else:
+        monkeypatch.setenv('REGTR_AGG_IMPL', impl)
     rng = np.random.default_rng(cin)
     Nq, Ns, K = 301, 457, 40
     q = rng.normal(size=(Nq, 3)).astype(np.float32) * 0.05
@@ -655,3 +659,106 @@ def test_staged_executor_matches_and_reports_stage_times():
     assert torch.equal(a['pose'], b['pose'])
     ms = four.stage_ms()
     assert list(ms) == ['preprocess', 'encoder', 'attention_decoder', 'pose'] and all(v > 0 for v in ms.values())
+
+
+# ------------------------------------------------- InstanceNorm statistics in the GEMM epilogue
+
+@pytest.mark.parametrize('lens,N,K', [([700, 1, 0, 333, 90], 64, 96),        # cloud boundaries inside 32-row groups, empty + 1-row clouds
+                                      ([4000, 4100], 128, 64),               # BN = 128 tiles, many m-tiles
+                                      ([300, 260], 256, 3840),               # split-K path (k_splitk_reduce_stats)
+                                      ([5000, 4000, 3000, 100], 32, 480)])   # BN = 32 contraction shape
+def test_gemm_instats_matches_float64(lens, N, K):
+    """regtr_gemm_tf32x3_instats: C and the per-cloud (mean, rstd) of C accumulated in the epilogue (fixed-point
+    integer atomics) vs float64; capacity padding rows (m_dev) excluded; bit-identical across repeated calls."""
+    from regtr_b200 import ops
+    rng = np.random.default_rng(N + K)
+    M = sum(lens)
+    cap = M + 200                                               # capacity-shaped launch with a device row count
+    a = np.zeros((cap, K), dtype=np.float32)
+    a[:M] = rng.normal(size=(M, K)) * 1.3 + 0.4
+    a[M:] = 1e3                                                 # garbage in the padding rows must not leak into the statistics
+    w = (rng.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32)
+    offs = ops.make_offsets(lens, DEV)
+    m_dev = offs[len(lens):len(lens) + 1]
+    hi, lo = ops.split_weight(G(w))
+    out, stats = ops.gemm_instats(G(a), hi, lo, offs, len(lens), m_dev=m_dev)
+    out2, stats2 = ops.gemm_instats(G(a), hi, lo, offs, len(lens), m_dev=m_dev)
+    assert torch.equal(stats, stats2) and torch.equal(out[:M], out2[:M])           # deterministic
+    c64 = a[:M].astype(np.float64) @ w.astype(np.float64).T
+    assert np.abs(N_(out)[:M] - c64).max() <= 1e-5 * np.abs(c64).max() * max(1.0, (K / 256) ** 0.5)
+    st = N_(stats)
+    starts = np.concatenate([[0], np.cumsum(lens)])
+    for c, n in enumerate(lens):
+        if n == 0:
+            continue
+        blk = c64[starts[c]:starts[c + 1]]
+        mean, var = blk.mean(0), blk.var(0)
+        np.testing.assert_allclose(st[c, :, 0], mean, rtol=0, atol=2e-6 * max(1.0, np.abs(c64).max()))
+        np.testing.assert_allclose(st[c, :, 1], 1.0 / np.sqrt(var + 1e-5), rtol=2e-5, atol=0)
+    # the fused pair (GEMM with statistics + apply) equals the separate-pass InstanceNorm
+    want = ops.instnorm_act(out[:M].contiguous(), offs, len(lens), slope=0.1)
+    got = ops.instnorm_apply(out[:M].contiguous(), offs, len(lens), stats, slope=0.1)
+    assert float((got - want).abs().max()) <= 5e-6
+
+
+def N_(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------- N1 + N2 through the GPU once (SURVEY.md 8f)
+
+def test_benchmark_loop_on_real_sample_pairs_through_graph_executor(tmp_path):
+    """The reference's test loop (generic_reg_model.py:130-183 -> benchmark_predator.py:285-375) on the two shipped
+    sample pairs that belong to the 3DMatch benchmark: `ThreeDMatchPairs` (files as the dataset stores them:
+    float64 .pth) -> `PairStream` (pinned read-ahead) -> `GraphedRegTR` -> `EstLogWriter` -> `benchmark_3dmatch`
+    against their real gt.log / gt.info entries.  Random weights: the recall is meaningless, but the est.log
+    must parse, hold the eager forward's poses and be scored; loader throughput is printed beside the model's."""
+    import json
+    import os
+    import pickle
+    import time
+    from conftest import GOLDEN
+    from regtr_b200 import data as D, eval as E
+    from regtr_b200.config import get_config
+    from regtr_b200.regtr import GraphedRegTR, RegTR
+    from regtr_b200.weights import random_state_dict
+    rows = json.load(open(os.path.join(GOLDEN, 'real', 'test_3DMatch_info_rows.json')))
+    infos = dict(rot=[], trans=[], src=[], tgt=[], overlap=[])
+    for r in rows:                                   # rebuild the on-disk layout: data/indoor/test/<scene>/cloud_bin_<i>.pth
+        inp = np.load(os.path.join(GOLDEN, 'real', r['fixture'] + '_input.npz'))
+        for rel in (r['src'], r['tgt']):
+            which = 'src_xyz' if os.path.basename(rel) == os.path.basename(str(inp['src_file'])) else 'tgt_xyz'
+            path = tmp_path / 'indoor' / rel
+            os.makedirs(path.parent, exist_ok=True)
+            torch.save(inp[which].astype(np.float64), path)
+        infos['rot'].append(np.array(r['rot'])); infos['trans'].append(np.array(r['trans']))
+        infos['src'].append(r['src']); infos['tgt'].append(r['tgt']); infos['overlap'].append(r['overlap'])
+    with open(tmp_path / 'info.pkl', 'wb') as f:
+        pickle.dump(infos, f)
+    ds = D.ThreeDMatchPairs(str(tmp_path / 'indoor'), str(tmp_path / 'info.pkl'), pin=True)
+    assert len(ds) == 2
+    cfg = get_config('3dmatch')
+    model = RegTR(cfg).to(DEV).eval()
+    model.load_state_dict(random_state_dict(cfg, 41), strict=True)
+    runner = GraphedRegTR(model)
+    gt_dir = os.path.join(GOLDEN, 'real', 'benchmarks', '3DMatch')
+    t0 = time.perf_counter()
+    res = E.run_3dmatch_benchmark(D.PairStream(ds, [[0], [1]], workers=2), lambda b: runner(b), str(tmp_path / 'log'),
+                                  '3DMatch', gt_dir)
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    n_loaded = sum(1 for _ in D.PairStream(ds, [[0], [1]] * 8, workers=4))
+    t_load = time.perf_counter() - t0
+    print(f'loader {n_loaded / t_load:.0f} pairs/s (pinned, 4 threads); loop incl. graph capture {t_all:.2f} s')
+    assert set(res['per_scene']) == {'7-scenes-redkitchen', 'sun3d-hotel_umd-maryland_hotel3'}
+    assert 'Mean median RRE' in res['summary'] and 0.0 <= res['recall'] <= 1.0
+    assert 'reg_success_final' in res['metrics']
+    for k, r in enumerate(rows):                     # est.log holds the eager forward's final-layer pose of each pair
+        scene = r['src'].split('/')[1]
+        pairs, traj = E.read_trajectory(os.path.join(str(tmp_path / 'log'), '3DMatch', scene, 'est.log'))
+        assert len(pairs) == 1 and traj.shape == (1, 4, 4)
+        item = ds[k]
+        want = model({'src_xyz': [item['src_xyz'].to(DEV)], 'tgt_xyz': [item['tgt_xyz'].to(DEV)]})['pose'][-1, 0].cpu().numpy()
+        assert np.abs(traj[0, :3] - want).max() <= 5e-5
+        assert np.allclose(traj[0, 3], [0, 0, 0, 1])
