@@ -55,7 +55,7 @@ def parse():
     ap.add_argument('--pairs', type=int, default=None, help='pairs per GPU per step (default: from config)')
     ap.add_argument('--cpu-baseline', type=int, default=1, help='time the CPU port beside the GPU run (N=1 only)')
     ap.add_argument('--checks', type=int, default=1, help='report pose error vs the oracle on one pair')
-    ap.add_argument('--attention', default='fp32', choices=['fp32', 'bf16_tc'],
+    ap.add_argument('--attention', default='fp32', choices=['fp32', 'tf32_tc', 'bf16_tc'],
                     help="fp32: parity kernel (default, pose within 1e-4); bf16_tc: tcgen05 tensor-core core")
     ap.add_argument('--inflight', type=int, default=10,
                     help='independent pairs in flight per GPU (CUDA-graph executors on private streams); 1 = serial')

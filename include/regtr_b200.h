@@ -162,15 +162,15 @@ int regtr_gemm_tf32x3(const float* A, int lda, const float* B_hi, const float* B
                       void* ws, size_t ws_bytes, void* stream);
 
 /* C = A @ B^T (no bias / residual / activation) PLUS the per-cloud InstanceNorm statistics of C:
- * stats (n_clouds, N, 2) = (mean, 1/sqrt(biased var + eps)) over the rows [offs[c], offs[c+1]) of each column.
- * Every epilogue warp reduces its 32 rows in a fixed shuffle tree and adds to 128-bit fixed-point accumulators
- * with 64-bit INTEGER atomics (associative: run-to-run bit-identical statistics); the launch's last CTA
- * finalises.  N % 32 == 0.  acc: regtr_instnorm_acc_bytes(n_clouds, N) bytes, 256-byte aligned, ZERO before the
- * first call and owned by this op between calls (every call leaves it zero). */
-size_t regtr_instnorm_acc_bytes(int n_clouds, int C);
+ * stats (n_clouds, N, 2) = (mean, 1/sqrt(biased var + eps)) over the rows [offs[c], offs[c+1]) of each column,
+ * without a second pass over C: every epilogue warp stores the column sums / sums of squares of its 32 rows
+ * (fixed shuffle tree) to `part`, and a small second kernel adds the partials of each cloud in a fixed order
+ * (fp64) -- no atomics, run-to-run bit-identical.  N % 32 == 0.
+ * part: regtr_instnorm_part_bytes(M, N) bytes of scratch (8-byte aligned; contents irrelevant on entry). */
+size_t regtr_instnorm_part_bytes(int M, int N);
 int regtr_gemm_tf32x3_instats(const float* A, int lda, const float* B_hi, const float* B_lo, int ldb,
                               float* C, int ldc, int M, int N, int K, const int32_t* m_dev,
-                              const int32_t* offs, int n_clouds, float eps, void* acc, float* stats,
+                              const int32_t* offs, int n_clouds, float eps, void* part, float* stats,
                               void* ws, size_t ws_bytes, void* stream);
 
 /* ---- transformer ------------------------------------------------------------------ */
@@ -229,6 +229,21 @@ int regtr_mha_bf16_tc_fwd(const void* QK, int ld_qk, const void* Vt, int ld_vt, 
                           int ldo, const int32_t* q_start, const int32_t* q_len, const int32_t* k_start,
                           const int32_t* k_len, int n_problems, int max_q_len, int n_heads, int head_dim,
                           float scale, void* stream);
+
+/* fp32-accurate attention core on the tcgen05 tensor cores (the parity mode of the same nn.MultiheadAttention core,
+ * transformers.py:197-226): S = Q K^T and O = P V as 3xTF32 tcgen05.mma with TMA-fed operands, P kept in tensor
+ * memory, fp32 softmax.  Inputs from regtr_gemm_tf32x3_qkv_split, the packed in-projection (N = 3E: q | k | v) whose
+ * epilogue writes every value as its two TF32 halves: qk4 [n_tokens, 4E] fp32 = [Q_hi | Q_lo | K_hi | K_lo] with q
+ * pre-multiplied by qscale (pass softmax_scale * log2(e)); vt2 [2E, ld_vt] fp32 = v transposed, hi rows then lo rows
+ * (columns >= the real token count must be finite, e.g. zero).  O [n_tokens, E] fp32.  head_dim must be 32.
+ * Problem tables as for regtr_mha_varlen_fwd. */
+int regtr_gemm_tf32x3_qkv_split(const float* A, int lda, const float* B_hi, const float* B_lo, int ldb,
+                                const float* bias, int M, int N, int K, int E, float qscale, float* qk4, int ld4,
+                                float* vt2, int ld_vt, const int32_t* m_dev, void* stream);
+int regtr_mha_tf32_tc_fwd(const float* qk4, int ld4, const float* vt2, int ld_vt, int n_tokens, float* O, int ldo,
+                          const int32_t* q_start, const int32_t* q_len, const int32_t* k_start,
+                          const int32_t* k_len, int n_problems, int max_q_len, int n_heads, int head_dim,
+                          void* stream);
 
 /* ---- pose ------------------------------------------------------------------------- */
 

@@ -46,7 +46,7 @@ SIGNATURES = {
     'regtr_instnorm_counter_bytes': (_Z, [_I, _I]),
     'regtr_instnorm_act': (_I, [_P, _P, _I, _I, _I, _F, _P, _F, _P, _P, _P, _Z, _P, _P]),
     'regtr_instnorm_apply': (_I, [_P, _P, _I, _I, _I, _P, _P, _F, _P, _P, _P]),
-    'regtr_instnorm_acc_bytes': (_Z, [_I, _I]),
+    'regtr_instnorm_part_bytes': (_Z, [_I, _I]),
     'regtr_gemm_tf32x3_instats': (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _F, _P, _P, _P, _Z, _P]),
     'regtr_split_tf32': (_I, [_P, _c.c_longlong, _P, _P, _P]),
     'regtr_gemm_ws_bytes': (_Z, [_I, _I, _I]),
@@ -58,6 +58,8 @@ SIGNATURES = {
     'regtr_mha_varlen_fwd': (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     'regtr_gemm_tf32x3_qkv_bf16': (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P]),
     'regtr_mha_bf16_tc_fwd': (_I, [_P, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    'regtr_gemm_tf32x3_qkv_split': (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _F, _P, _I, _P, _I, _P, _P]),
+    'regtr_mha_tf32_tc_fwd': (_I, [_P, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     'regtr_kabsch_fwd': (_I, [_P, _P, _P, _P, _I, _P, _P]),
     'regtr_pose_from_corr': (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
     'regtr_status_clear': (_I, [_P, _P]),

@@ -344,8 +344,8 @@ def gemm(a, b_hi, b_lo, bias=None, residual=None, relu=False, m_dev=None, out=No
 
 
 def gemm_instats(a, b_hi, b_lo, offs, n_clouds: int, eps: float = 1e-5, m_dev=None, out=None):
-    """a @ B^T plus the per-cloud InstanceNorm statistics of the result, accumulated in the GEMM epilogue
-    (deterministic fixed-point integer atomics).  -> (out (M,N), stats (n_clouds, N, 2) = (mean, rstd))."""
+    """a @ B^T plus the per-cloud InstanceNorm statistics of the result: 32-row partial sums from the GEMM
+    epilogue + a small fixed-order finalisation (no atomics).  -> (out (M,N), stats (n_clouds, N, 2) = (mean, rstd))."""
     L = _lib.load()
     if not a.is_cuda or a.dtype != torch.float32 or a.dim() != 2 or a.stride(1) != 1:
         raise ValueError('gemm: A must be a CUDA fp32 matrix with unit column stride')
@@ -355,14 +355,14 @@ def gemm_instats(a, b_hi, b_lo, offs, n_clouds: int, eps: float = 1e-5, m_dev=No
     stats = torch.empty((n_clouds, N, 2), dtype=torch.float32, device=a.device)
     nb = L.regtr_gemm_ws_bytes(M, N, K)
     ws = workspace(nb, a.device, 'gemm')
-    acc = workspace(L.regtr_instnorm_acc_bytes(n_clouds, N), a.device, 'instnorm_acc', zero=True)
+    acc = workspace(L.regtr_instnorm_part_bytes(M, N), a.device, 'instnorm_part')
     if TRACE is not None:
         TRACE.append(('gemm', dict(M=M, N=N, K=K, split_k=nb > 256, instats=True),
                       lambda: gemm_instats(a, b_hi, b_lo, offs, n_clouds, eps, m_dev=m_dev, out=out)))
     _lib.check(L.regtr_gemm_tf32x3_instats(_p(a), a.stride(0), _p(b_hi), _p(b_lo), b_hi.stride(0), _p(out), out.stride(0),
                                            M, N, K, _p(m_dev), _p(offs), n_clouds, float(eps), _p(acc), _p(stats),
                                            _p(ws), ws.numel(), _stream()), 'regtr_gemm_tf32x3_instats')
-    _count(2 if nb > 256 else 1)
+    _count(3 if nb > 256 else 2)
     return out, stats
 
 
@@ -497,6 +497,39 @@ def mha_bf16_tc(x, in_w, in_b, q_start, q_len, k_start, k_len, max_q_len: int, n
     _lib.check(L.regtr_mha_bf16_tc_fwd(_p(qk), 2 * E, _p(vt), ld_vt, N, _p(out), E, _p(q_start), _p(q_len),
                                        _p(k_start), _p(k_len), q_start.numel(), int(max_q_len), n_heads, dh,
                                        1.0 / math.sqrt(dh), _stream()), 'regtr_mha_bf16_tc_fwd')
+    _count(2)
+    return out
+
+
+def mha_tf32_tc(x, in_w, in_b, q_start, q_len, k_start, k_len, max_q_len: int, n_heads: int, m_dev=None):
+    """Attention block core, fp32-accurate, on the tcgen05 tensor cores: packed in-projection (3xTF32 GEMM whose
+    epilogue writes q / k / v^T as TF32 (hi, lo) halves) + the TMA-fed 3xTF32 attention kernel (P in tensor memory).
+    x (N,E) fp32 (already LN + pos); returns O (N,E) fp32."""
+    L = _lib.load()
+    _chk(x, torch.float32, 'x', 2)
+    N, E = x.shape
+    dh = E // n_heads
+    hi, lo = split_weight(in_w)
+    ld_vt = (N + 63) // 64 * 64 + 64            # token pitch of the transposed V (16-byte multiple, tile over-read)
+    qk4 = torch.empty((N, 4 * E), dtype=torch.float32, device=x.device)
+    vt2 = torch.zeros((2 * E, ld_vt), dtype=torch.float32, device=x.device)     # padding tokens must stay finite
+    qscale = (1.0 / math.sqrt(dh)) * 1.4426950408889634
+    _lib.check(L.regtr_gemm_tf32x3_qkv_split(_p(x), x.stride(0), _p(hi), _p(lo), hi.stride(0), _p(in_b), N, 3 * E, E, E,
+                                             float(qscale), _p(qk4), 4 * E, _p(vt2), ld_vt, _p(m_dev), _stream()),
+               'regtr_gemm_tf32x3_qkv_split')
+    out = torch.empty((N, E), dtype=torch.float32, device=x.device)
+    if TRACE is not None:
+        ql, kl = q_len.tolist(), k_len.tolist()
+        TRACE.append(('gemm', dict(M=N, N=3 * E, K=E, split_k=False, qkv_split=True), lambda: L.regtr_gemm_tf32x3_qkv_split(
+            _p(x), x.stride(0), _p(hi), _p(lo), hi.stride(0), _p(in_b), N, 3 * E, E, E, float(qscale), _p(qk4), 4 * E,
+            _p(vt2), ld_vt, _p(m_dev), _stream())))
+        TRACE.append(('mha', dict(pairs_qk=sum(a * b for a, b in zip(ql, kl)), E=E, tokens=sum(ql)),
+                      lambda: L.regtr_mha_tf32_tc_fwd(_p(qk4), 4 * E, _p(vt2), ld_vt, N, _p(out), E, _p(q_start), _p(q_len),
+                                                      _p(k_start), _p(k_len), q_start.numel(), int(max_q_len), n_heads, dh,
+                                                      _stream())))
+    _lib.check(L.regtr_mha_tf32_tc_fwd(_p(qk4), 4 * E, _p(vt2), ld_vt, N, _p(out), E, _p(q_start), _p(q_len),
+                                       _p(k_start), _p(k_len), q_start.numel(), int(max_q_len), n_heads, dh, _stream()),
+               'regtr_mha_tf32_tc_fwd')
     _count(2)
     return out
 

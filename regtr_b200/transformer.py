@@ -123,8 +123,8 @@ class TransformerCrossEncoderLayer(nn.Module):
                  normalize_before=False, sa_val_has_pos_emb=False, ca_val_has_pos_emb=False,
                  attention_type='dot_prod', attention_impl='fp32'):
         super().__init__()
-        if attention_impl not in ('fp32', 'bf16_tc'):
-            raise ValueError("attention_impl must be 'fp32' (parity) or 'bf16_tc' (tcgen05 tensor cores)")
+        if attention_impl not in ('fp32', 'tf32_tc', 'bf16_tc'):
+            raise ValueError("attention_impl: 'tf32_tc' (tcgen05 3xTF32, fp32-accurate), 'fp32' (mma.sync 3xTF32) or 'bf16_tc'")
         self.attention_impl = attention_impl
         if attention_type != 'dot_prod':
             raise NotImplementedError
@@ -151,6 +151,10 @@ class TransformerCrossEncoderLayer(nn.Module):
         if self.attention_impl == 'bf16_tc' and val_has_pos:
             # fast mode: in-projection with a bf16 epilogue + tcgen05 attention core (TMA-fed, TMEM accumulators)
             return ops.mha_bf16_tc(x2p, W, b, plan.q_start, plan.q_len, ks, kl, plan.max_len, self.nhead,
+                                   m_dev=plan.n_dev)
+        if self.attention_impl == 'tf32_tc' and val_has_pos:
+            # parity mode on the Blackwell path: split-epilogue in-projection + TMA-fed tcgen05 3xTF32 attention core
+            return ops.mha_tf32_tc(x2p, W, b, plan.q_start, plan.q_len, ks, kl, plan.max_len, self.nhead,
                                    m_dev=plan.n_dev)
         nd = plan.n_dev
         if val_has_pos:
