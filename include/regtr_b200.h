@@ -38,6 +38,7 @@ extern "C" {
 
 #define REGTR_STATUS_KEY_RANGE 1u /* a voxel / cell coordinate left the 16-bit key range */
 #define REGTR_STATUS_CAPACITY 2u  /* a capacity-bounded output (sub-sampled level) overflowed; results truncated */
+#define REGTR_STATUS_GRID 4u      /* voxel bounding box beyond the dense-grid budget: redo with regtr_grid_subsample_sorted */
 
 int regtr_version(void);                 /* ABI version, currently 1 */
 const char* regtr_build_info(void);      /* host pointer: arch + compile flags string */
@@ -53,10 +54,20 @@ const char* regtr_build_info(void);      /* host pointer: arch + compile flags s
  * out_cap may be smaller than n_cap (static-shape pipelines): on overflow the output is
  * truncated memory-safely and REGTR_STATUS_CAPACITY is raised.
  * status: device uint32 word, OR-ed with REGTR_STATUS_* on data-dependent errors. */
-size_t regtr_grid_subsample_ws_bytes(int n_cap);
+size_t regtr_grid_subsample_ws_bytes(int n_cap, int n_clouds);
+size_t regtr_grid_subsample_state_bytes(int n_cap);
 int regtr_grid_subsample(const float* xyz, const int32_t* offs, int n_clouds, int n_cap, float dl,
                          float* out_xyz, int out_cap, int32_t* out_offs, uint32_t* status,
-                         void* ws, size_t ws_bytes, void* stream);
+                         void* ws, size_t ws_bytes, void* state, size_t state_bytes, void* stream);
+/* regtr_grid_subsample sorts by COUNTING over a dense voxel grid spanning each cloud's bounding box (hand-written
+ * kernels only; budget: 16 cells per point of capacity, at least 2^18).  `state`: regtr_grid_subsample_state_bytes
+ * bytes, ZERO before the first call and owned by this op between calls (every call leaves it zero).  A box beyond
+ * the budget raises REGTR_STATUS_GRID; regtr_grid_subsample_sorted (stable library radix sort of (key, index)
+ * pairs, any extent) gives the same result for such inputs. */
+size_t regtr_grid_subsample_sorted_ws_bytes(int n_cap);
+int regtr_grid_subsample_sorted(const float* xyz, const int32_t* offs, int n_clouds, int n_cap, float dl,
+                                float* out_xyz, int out_cap, int32_t* out_offs, uint32_t* status,
+                                void* ws, size_t ws_bytes, void* stream);
 
 /* Uniform cell list over a stacked point set (search structure for regtr_ball_query).
  * `grid` is an opaque caller-owned buffer of regtr_cellgrid_bytes(n_cap) bytes; `order`
@@ -64,9 +75,10 @@ int regtr_grid_subsample(const float* xyz, const int32_t* offs, int n_clouds, in
  * coherent processing order for queries drawn from the same set). */
 size_t regtr_cellgrid_bytes(int n_cap);
 size_t regtr_cellgrid_ws_bytes(int n_cap);
+size_t regtr_cellgrid_state_bytes(int n_cap);   /* ZERO before the first call; every call leaves it zero */
 int regtr_cellgrid_build(const float* xyz, const int32_t* offs, int n_clouds, int n_cap, float cell,
                          void* grid, int32_t* order, uint32_t* status,
-                         void* ws, size_t ws_bytes, void* stream);
+                         void* ws, size_t ws_bytes, void* state, size_t state_bytes, void* stream);
 
 /* Fixed-radius neighbour search, first K supports in ascending index order.
  * Replaces batch_neighbors_kpconv_gpu (kpconv.py:261-288: pytorch3d 0.6.0 packed_to_padded +
@@ -189,8 +201,10 @@ int regtr_layernorm_pos(const float* x, const float* gamma, const float* beta, c
                         int n, const int32_t* n_dev, int E, float eps, float* y, float* y_pos, void* stream);
 
 /* Device-side attention problem table for a (src x B, tgt x B) token stack with cloud offsets
- * offs (2B+1): plan (4, 2B) i32 rows = q_start, q_len, cross k_start, cross k_len (the cross
- * partner of src_b is tgt_b and vice versa; regtr.py:156-166's key-padding masks made explicit). */
+ * offs (2B+1): plan (6, 2B+1) i32 rows = q_start, q_len, cross k_start, cross k_len (the cross
+ * partner of src_b is tgt_b and vice versa; regtr.py:156-166's key-padding masks made explicit), then the
+ * exclusive prefix of the number of 64-query / 128-query tiles per problem (entry 2B = total): the `tile_base`
+ * tables of the attention kernels below. */
 int regtr_attention_plan(const int32_t* offs, int B, int32_t* plan, void* stream);
 
 /* Variable-length multi-head attention core, fp32:  O = softmax(Q K^T * scale) V per head.
@@ -203,7 +217,11 @@ int regtr_attention_plan(const int32_t* offs, int B, int32_t* plan, void* stream
 int regtr_mha_varlen_fwd(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
                          float* O, int ldo, const int32_t* q_start, const int32_t* q_len,
                          const int32_t* k_start, const int32_t* k_len, int n_problems,
-                         int max_q_len, int n_heads, int head_dim, float scale, void* stream);
+                         int max_q_len, const int32_t* tile_base, int max_tiles,
+                         int n_heads, int head_dim, float scale, void* stream);
+/* tile_base (optional, n_problems + 1, device): exclusive prefix of ceil(q_len / 64) with the total last; the launch
+ * then covers max_tiles (a host bound of that total, e.g. capacity / 64 + n_problems) linear tiles instead of
+ * ceil(max_q_len / 64) tiles per problem -- capacity-shaped launches know the per-problem lengths on the device only. */
 
 /* CorrespondenceDecoder.simple_attention (regtr.py:316-351, the `direct_regress_coor: False` branch):
  * single-head attention whose values are the key coordinates,
@@ -242,8 +260,9 @@ int regtr_gemm_tf32x3_qkv_split(const float* A, int lda, const float* B_hi, cons
                                 float* vt2, int ld_vt, const int32_t* m_dev, void* stream);
 int regtr_mha_tf32_tc_fwd(const float* qk4, int ld4, const float* vt2, int ld_vt, int n_tokens, float* O, int ldo,
                           const int32_t* q_start, const int32_t* q_len, const int32_t* k_start,
-                          const int32_t* k_len, int n_problems, int max_q_len, int n_heads, int head_dim,
-                          void* stream);
+                          const int32_t* k_len, int n_problems, int max_q_len, const int32_t* tile_base,
+                          int max_tiles, int n_heads, int head_dim, void* stream);
+/* (tile_base / max_tiles as for regtr_mha_varlen_fwd, with 128-query tiles.) */
 
 /* ---- pose ------------------------------------------------------------------------- */
 

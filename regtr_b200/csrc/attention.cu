@@ -18,6 +18,16 @@
 namespace {
 
 constexpr int HD = 32;        // head dim
+
+// linear tile index -> (problem, tile inside the problem); false beyond the last tile
+__device__ __forceinline__ bool find_tile(const int32_t* __restrict__ tile_base, int n_prob, int& prob, int& tile) {
+    if (tile >= tile_base[n_prob]) return false;
+    int p = 0;
+    while (p + 1 < n_prob && tile_base[p + 1] <= tile) ++p;
+    prob = p;
+    tile -= tile_base[p];
+    return true;
+}
 constexpr int QT = 32;        // queries per block
 constexpr int KSPLIT = 4;     // warps per block
 constexpr int KT = 128;       // keys per shared-memory tile
@@ -144,9 +154,11 @@ __global__ void __launch_bounds__(128)
 k_mha_tf32x3(const float* __restrict__ Q, int ldq, const float* __restrict__ Kp, int ldk, const float* __restrict__ Vp,
              int ldv, float* __restrict__ O, int ldo, const int32_t* __restrict__ q_start,
              const int32_t* __restrict__ q_len, const int32_t* __restrict__ k_start, const int32_t* __restrict__ k_len,
-             float scale) {
+             const int32_t* __restrict__ tile_base, int n_prob, float scale) {
     __shared__ __align__(16) float sKh[MK][MLD], sKl[MK][MLD], sVh[MK][MLD], sVl[MK][MLD];
-    const int prob = blockIdx.z, head = blockIdx.y, tile = blockIdx.x;
+    int prob = blockIdx.z, tile = blockIdx.x;
+    const int head = blockIdx.y;
+    if (tile_base && !find_tile(tile_base, n_prob, prob, tile)) return;
     const int ql = q_len[prob];
     if (tile * MQ >= ql) return;
     const int q0 = q_start[prob], k0 = k_start[prob], kl = k_len[prob];
@@ -164,7 +176,7 @@ k_mha_tf32x3(const float* __restrict__ Q, int ldq, const float* __restrict__ Kp,
             const float v[4] = {p0[8 * kk + t] * scale, p1[8 * kk + t] * scale, p0[8 * kk + t + 4] * scale,
                                 p1[8 * kk + t + 4] * scale};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { qh[kk][e] = tf32_head(v[e]); qlo[kk][e] = __float_as_uint(v[e] - __uint_as_float(qh[kk][e])); }
+            for (int e = 0; e < 4; ++e) { qh[kk][e] = tf32_head(v[e]); qlo[kk][e] = tf32_head(v[e] - __uint_as_float(qh[kk][e])); }
         }
     }
     float acc[4][4];
@@ -189,8 +201,9 @@ k_mha_tf32x3(const float* __restrict__ Q, int ldq, const float* __restrict__ Kp,
             float kh[4], kl4[4], vh[4], vl4[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                kh[e] = __uint_as_float(tf32_head(kx[e])); kl4[e] = kx[e] - kh[e];
-                vh[e] = __uint_as_float(tf32_head(vx[e])); vl4[e] = vx[e] - vh[e];
+                // lo halves rounded to nearest TF32 too: the tensor core would truncate them (a one-sided bias)
+                kh[e] = __uint_as_float(tf32_head(kx[e])); kl4[e] = __uint_as_float(tf32_head(kx[e] - kh[e]));
+                vh[e] = __uint_as_float(tf32_head(vx[e])); vl4[e] = __uint_as_float(tf32_head(vx[e] - vh[e]));
             }
             *reinterpret_cast<float4*>(&sKh[r][4 * c4]) = make_float4(kh[0], kh[1], kh[2], kh[3]);
             *reinterpret_cast<float4*>(&sKl[r][4 * c4]) = make_float4(kl4[0], kl4[1], kl4[2], kl4[3]);
@@ -236,30 +249,40 @@ k_mha_tf32x3(const float* __restrict__ Q, int ldq, const float* __restrict__ Kp,
         m0 = mn0; m1 = mn1;
         l0 *= c0; l1 *= c1;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[j][0] *= c0; acc[j][1] *= c0; acc[j][2] *= c1; acc[j][3] *= c1; }
-#pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             S[nt][0] = fast_exp2(S[nt][0] - mn0); S[nt][1] = fast_exp2(S[nt][1] - mn0);
             S[nt][2] = fast_exp2(S[nt][2] - mn1); S[nt][3] = fast_exp2(S[nt][3] - mn1);
             l0 += S[nt][0] + S[nt][1];
             l1 += S[nt][2] + S[nt][3];
         }
-        // O += P V
+        // O = O * c + P V.  The chunk's P V is accumulated from zero and added to the running output with a
+        // round-to-nearest FMA: the tensor core truncates when it adds into its accumulator, and a chain through
+        // every key of a 700-token cloud (264 MMAs) biased the outputs by ~1e-5 relative (tests/diag_accuracy.py).
+        float pacc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pacc[j][e] = 0.f;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
             // A fragment of P: a0 (r0, key 2t) a1 (r1, key 2t) a2 (r0, key 2t+1) a3 (r1, key 2t+1)
             const float pv[4] = {S[nt][0], S[nt][2], S[nt][1], S[nt][3]};
             uint32_t ph[4], pl[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { ph[e] = tf32_head(pv[e]); pl[e] = __float_as_uint(pv[e] - __uint_as_float(ph[e])); }
+            for (int e = 0; e < 4; ++e) { ph[e] = tf32_head(pv[e]); pl[e] = tf32_head(pv[e] - __uint_as_float(ph[e])); }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t bh0 = __float_as_uint(sVh[8 * nt + 2 * t][8 * j + g]), bh1 = __float_as_uint(sVh[8 * nt + 2 * t + 1][8 * j + g]);
                 const uint32_t bl0 = __float_as_uint(sVl[8 * nt + 2 * t][8 * j + g]), bl1 = __float_as_uint(sVl[8 * nt + 2 * t + 1][8 * j + g]);
-                mma_tf32(acc[j], pl, bh0, bh1);
-                mma_tf32(acc[j], ph, bl0, bl1);
-                mma_tf32(acc[j], ph, bh0, bh1);
+                mma_tf32(pacc[j], pl, bh0, bh1);
+                mma_tf32(pacc[j], ph, bl0, bl1);
+                mma_tf32(pacc[j], ph, bh0, bh1);
             }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc[j][0] = fmaf(acc[j][0], c0, pacc[j][0]); acc[j][1] = fmaf(acc[j][1], c0, pacc[j][1]);
+            acc[j][2] = fmaf(acc[j][2], c1, pacc[j][2]); acc[j][3] = fmaf(acc[j][3], c1, pacc[j][3]);
         }
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -367,17 +390,31 @@ k_corr_attention(const float* __restrict__ Qp, const float* __restrict__ Kp, int
     }
 }
 
-// plan[0..4)[c]: q_start, q_len, cross k_start, cross k_len for cloud c of a (src x B, tgt x B) stack.
+// plan rows (pitch 2B + 1): q_start, q_len, cross k_start, cross k_len for cloud c of a (src x B, tgt x B) stack,
+// then the exclusive prefix of the number of 64-query and 128-query tiles per problem (entry 2B = total): the
+// attention kernels are launched over a LINEAR tile index and find their problem in this table, so that a
+// capacity-shaped launch (the per-cloud lengths live on the device) does not pay for max_len / tile empty CTAs
+// per problem.
 __global__ void k_attention_plan(const int32_t* __restrict__ offs, int B, int32_t* __restrict__ plan) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n2 = 2 * B;
-    if (c >= n2) return;
-    const int o = c < B ? c + B : c - B;
-    plan[0 * n2 + c] = offs[c];
-    plan[1 * n2 + c] = offs[c + 1] - offs[c];
-    plan[2 * n2 + c] = offs[o];
-    plan[3 * n2 + c] = offs[o + 1] - offs[o];
+    const int n2 = 2 * B, ld = n2 + 1;
+    for (int c = threadIdx.x; c < n2; c += blockDim.x) {
+        const int o = c < B ? c + B : c - B;
+        plan[0 * ld + c] = offs[c];
+        plan[1 * ld + c] = offs[c + 1] - offs[c];
+        plan[2 * ld + c] = offs[o];
+        plan[3 * ld + c] = offs[o + 1] - offs[o];
+    }
+    if (threadIdx.x == 0) {
+        int t64 = 0, t128 = 0;
+        for (int c = 0; c < n2; ++c) {
+            const int l = offs[c + 1] - offs[c];
+            plan[4 * ld + c] = t64; plan[5 * ld + c] = t128;
+            t64 += (l + 63) >> 6; t128 += (l + 127) >> 7;
+        }
+        plan[4 * ld + n2] = t64; plan[5 * ld + n2] = t128;
+    }
 }
+
 
 }  // namespace
 
@@ -385,7 +422,7 @@ extern "C" int regtr_attention_plan(const int32_t* offs, int B, int32_t* plan, v
     if (B < 0) return REGTR_ERR_ARG;
     if (B == 0) return REGTR_OK;
     if (!offs || !plan) return REGTR_ERR_ARG;
-    k_attention_plan<<<regtr_cdiv(2 * B, 128), 128, 0, (cudaStream_t)stream_>>>(offs, B, plan);
+    k_attention_plan<<<1, 128, 0, (cudaStream_t)stream_>>>(offs, B, plan);
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
 }
@@ -393,18 +430,21 @@ extern "C" int regtr_attention_plan(const int32_t* offs, int B, int32_t* plan, v
 extern "C" int regtr_mha_varlen_fwd(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
                                     float* O, int ldo, const int32_t* q_start, const int32_t* q_len,
                                     const int32_t* k_start, const int32_t* k_len, int n_problems, int max_q_len,
-                                    int n_heads, int head_dim, float scale, void* stream_) {
+                                    const int32_t* tile_base, int max_tiles, int n_heads, int head_dim, float scale,
+                                    void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
-    if (n_problems < 0 || max_q_len < 0 || n_heads <= 0) return REGTR_ERR_ARG;
+    if (n_problems < 0 || max_q_len < 0 || n_heads <= 0 || max_tiles < 0) return REGTR_ERR_ARG;
     if (head_dim != HD) return REGTR_ERR_UNSUPPORTED;
-    if (n_problems == 0 || max_q_len == 0) return REGTR_OK;
+    if (n_problems == 0 || max_q_len == 0 || (tile_base && max_tiles == 0)) return REGTR_OK;
     if (!Q || !K || !V || !O || !q_start || !q_len || !k_start || !k_len) return REGTR_ERR_ARG;
     if ((ldq | ldk | ldv) % 4 != 0 || n_problems > 65535 || n_heads > 65535) return REGTR_ERR_ARG;
     const char* impl = getenv("REGTR_MHA_IMPL");           // "ffma": CUDA-core kernel (A/B measurements)
     if (!(impl && impl[0] == 'f') && (ldo % 2) == 0) {
-        dim3 grid(regtr_cdiv(max_q_len, MQ), n_heads, n_problems);
-        k_mha_tf32x3<<<grid, 128, 0, st>>>(Q, ldq, K, ldk, V, ldv, O, ldo, q_start, q_len, k_start, k_len,
-                                          scale * 1.4426950408889634f);
+        // with the tile table: linear 64-query tile index (max_tiles = host bound of the total); else one grid
+        // column per problem sized by the longest sequence
+        const dim3 grid = tile_base ? dim3(max_tiles, n_heads, 1) : dim3(regtr_cdiv(max_q_len, MQ), n_heads, n_problems);
+        k_mha_tf32x3<<<grid, 128, 0, st>>>(Q, ldq, K, ldk, V, ldv, O, ldo, q_start, q_len, k_start, k_len, tile_base,
+                                          n_problems, scale * 1.4426950408889634f);
         REGTR_CHECK_LAUNCH();
         return REGTR_OK;
     }

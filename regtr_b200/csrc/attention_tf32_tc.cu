@@ -30,7 +30,7 @@ namespace {
 constexpr int HD = 32;          // head dim (floats: one 128-byte swizzle row)
 constexpr int BQ = 128;         // queries per CTA
 constexpr int BKEY = 64;        // keys per tile
-constexpr int TMEM_COLS = 256;  // S0 / P_hi0 [0,64)  S1 / P_hi1 [64,128)  P_lo [128,192)  O [192,224)
+constexpr int TMEM_COLS = 256;  // S0 / P_hi0 [0,64)  S1 / P_hi1 [64,128)  P_lo [128,192)  O even tiles [192,224)  O odd tiles [224,256)
 constexpr uint32_t COL_PLO = 128, COL_O = 192;
 
 constexpr int Q_BYTES = BQ * HD * 4;        // 16 KB per half (hi / lo)
@@ -41,15 +41,25 @@ constexpr int SMEM_BYTES = 2 * Q_BYTES + 2 * STAGE_BYTES + 1024 + 256;
 constexpr uint32_t HI_MASK = 0xFFFFE000u;
 
 __device__ __forceinline__ uint32_t tf32_rn(float x) { return (__float_as_uint(x) + 0x1000u) & HI_MASK; }
+__device__ __forceinline__ float fast_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 __global__ void __launch_bounds__(192, 2)
 k_mha_tf32_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmVt, float* __restrict__ O, int ldo, int E,
               const int32_t* __restrict__ q_start, const int32_t* __restrict__ q_len,
-              const int32_t* __restrict__ k_start, const int32_t* __restrict__ k_len) {
+              const int32_t* __restrict__ k_start, const int32_t* __restrict__ k_len,
+              const int32_t* __restrict__ tile_base, int n_prob) {
     extern __shared__ unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int prob = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
+    int prob = blockIdx.z, qt = blockIdx.x;
+    const int head = blockIdx.y;
+    if (tile_base) {                                             // linear 128-query tile index -> (problem, tile)
+        if (qt >= tile_base[n_prob]) return;
+        int p = 0;
+        while (p + 1 < n_prob && tile_base[p + 1] <= qt) ++p;
+        prob = p;
+        qt -= tile_base[p];
+    }
     const int ql = q_len[prob];
     if (qt * BQ >= ql) return;                                   // uniform exit
     const int q0 = q_start[prob] + qt * BQ, k0 = k_start[prob], kl = k_len[prob];
@@ -179,9 +189,12 @@ k_mha_tf32_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                         const uint64_t adv = (uint64_t)(2 * (k & 3));
                         const uint64_t dVhi = tc::umma_desc_sw128_kmajor(tc::smem_u32(sVhi(s, h))) + adv;
                         const uint64_t dVlo = tc::umma_desc_sw128_kmajor(tc::smem_u32(sVlo(s, h))) + adv;
-                        tc::umma_tf32_ts(tmem + COL_O, p_lo + 8 * k, dVhi, idesc_o, (j | k) != 0);
-                        tc::umma_tf32_ts(tmem + COL_O, p_hi + 8 * k, dVlo, idesc_o, 1);
-                        tc::umma_tf32_ts(tmem + COL_O, p_hi + 8 * k, dVhi, idesc_o, 1);
+                        // two output accumulators (even / odd key tiles), added in the epilogue: the tensor core
+                        // truncates when it accumulates, and the bias grows with the length of the chain
+                        const uint32_t o_acc = tmem + COL_O + (uint32_t)(32 * (j & 1));
+                        tc::umma_tf32_ts(o_acc, p_lo + 8 * k, dVhi, idesc_o, ((j >> 1) | k) != 0);
+                        tc::umma_tf32_ts(o_acc, p_hi + 8 * k, dVlo, idesc_o, 1);
+                        tc::umma_tf32_ts(o_acc, p_hi + 8 * k, dVhi, idesc_o, 1);
                     }
                     tc::umma_commit(&pv_done[s]);
                     tc::umma_commit(&kv_empty[s]);
@@ -213,23 +226,34 @@ k_mha_tf32_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 for (int j = 0; j < BKEY; ++j) if (j >= jlo && j < jhi) m = fmaxf(m, v[j]);
             } else {
                 const int jt = it - n_kt;
-                // P_lo is single buffered: the PV MMAs of the previous pass-2 tile must have retired
-                if (jt >= 1) tc::mbar_wait(&pv_done[s ^ 1], ((jt - 1) >> 1) & 1);
-                tc::fence_after_thread_sync();
                 const uint32_t dst_hi = tmem + lane_addr + (uint32_t)(s * BKEY), dst_lo = tmem + lane_addr + COL_PLO;
+                // sweep 1: p = exp2(s - m) (kept in v[]), row sum, P_hi over the S columns this thread just read --
+                // no hazard with the PV MMAs of the previous tile, which read the OTHER S / P_hi buffer
 #pragma unroll
                 for (int c = 0; c < BKEY / 16; ++c) {
-                    uint32_t hi[16], lo[16];
+                    uint32_t hi[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         const int j = 16 * c + e;
-                        const float p = (j >= jlo && j < jhi) ? exp2f(v[j] - m) : 0.f;
+                        const float p = (j >= jlo && j < jhi) ? fast_exp2(v[j] - m) : 0.f;
                         l += p;
-                        const uint32_t h = tf32_rn(p);
-                        hi[e] = h;
-                        lo[e] = tf32_rn(p - __uint_as_float(h));
+                        v[j] = p;
+                        hi[e] = tf32_rn(p);
                     }
-                    tc::tmem_st_32x16(dst_hi + 16 * c, hi);     // P_hi over the S columns this thread just read
+                    tc::tmem_st_32x16(dst_hi + 16 * c, hi);
+                }
+                // P_lo is single buffered: the PV MMAs of the previous pass-2 tile must have retired before it is
+                // overwritten (the exponentials above ran while they executed)
+                if (jt >= 1) tc::mbar_wait(&pv_done[s ^ 1], ((jt - 1) >> 1) & 1);
+                tc::fence_after_thread_sync();
+#pragma unroll
+                for (int c = 0; c < BKEY / 16; ++c) {
+                    uint32_t lo[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const float p = v[16 * c + e];
+                        lo[e] = tf32_rn(p - __uint_as_float(tf32_rn(p)));
+                    }
                     tc::tmem_st_32x16(dst_lo + 16 * c, lo);
                 }
                 tc::tmem_st_wait();
@@ -242,6 +266,12 @@ k_mha_tf32_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         tc::fence_after_thread_sync();
         float o[HD];
         tc::tmem_ld_32x32(tmem + lane_addr + COL_O, o);
+        if (n_kt > 1) {                                          // odd tiles' accumulator (never written otherwise)
+            float o1[HD];
+            tc::tmem_ld_32x32(tmem + lane_addr + COL_O + 32, o1);
+#pragma unroll
+            for (int j = 0; j < HD; ++j) o[j] += o1[j];
+        }
         if (qt * BQ + row < ql) {
             const float inv = l > 0.f ? 1.f / l : 0.f;
             float4* dst = reinterpret_cast<float4*>(O + (size_t)(q0 + row) * ldo + head * HD);
@@ -287,12 +317,12 @@ bool make_map_f32(CUtensorMap* m, const void* ptr, long long rows, long long col
 
 extern "C" int regtr_mha_tf32_tc_fwd(const float* qk4, int ld4, const float* vt2, int ld_vt, int n_tokens, float* O,
                                      int ldo, const int32_t* q_start, const int32_t* q_len, const int32_t* k_start,
-                                     const int32_t* k_len, int n_problems, int max_q_len, int n_heads, int head_dim,
-                                     void* stream_) {
+                                     const int32_t* k_len, int n_problems, int max_q_len, const int32_t* tile_base,
+                                     int max_tiles, int n_heads, int head_dim, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
-    if (n_problems < 0 || max_q_len < 0 || n_heads <= 0 || n_tokens < 0) return REGTR_ERR_ARG;
+    if (n_problems < 0 || max_q_len < 0 || n_heads <= 0 || n_tokens < 0 || max_tiles < 0) return REGTR_ERR_ARG;
     if (head_dim != HD) return REGTR_ERR_UNSUPPORTED;
-    if (n_problems == 0 || max_q_len == 0 || n_tokens == 0) return REGTR_OK;
+    if (n_problems == 0 || max_q_len == 0 || n_tokens == 0 || (tile_base && max_tiles == 0)) return REGTR_OK;
     if (!qk4 || !vt2 || !O || !q_start || !q_len || !k_start || !k_len) return REGTR_ERR_ARG;
     const int E = n_heads * HD;
     if ((ld4 & 3) || (ld_vt & 3) || ld4 < 4 * E || ((uintptr_t)qk4 & 15) || ((uintptr_t)vt2 & 15) || (ldo & 3) ||
@@ -308,8 +338,9 @@ extern "C" int regtr_mha_tf32_tc_fwd(const float* qk4, int ld4, const float* vt2
         if (e != cudaSuccess) return -(1000 + (int)e);
         attr_set = true;
     }
-    dim3 grid(regtr_cdiv(max_q_len, BQ), n_heads, n_problems);
-    k_mha_tf32_tc<<<grid, 192, SMEM_BYTES, st>>>(tQ, tK, tV, O, ldo, E, q_start, q_len, k_start, k_len);
+    const dim3 grid = tile_base ? dim3(max_tiles, n_heads, 1) : dim3(regtr_cdiv(max_q_len, BQ), n_heads, n_problems);
+    k_mha_tf32_tc<<<grid, 192, SMEM_BYTES, st>>>(tQ, tK, tV, O, ldo, E, q_start, q_len, k_start, k_len, tile_base,
+                                                 n_problems);
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
 }

@@ -44,6 +44,15 @@ def level_capacities(cfg, cap0: int, ratio: float = 0.40, quantum: int = 256):
     return caps
 
 
+# InstanceNorm statistics from the producing GEMM's epilogue (32-row partial sums); False: the stand-alone
+# two-pass statistics kernel (A/B accuracy and timing measurements, tests/diag_accuracy.py)
+EPILOGUE_STATS = True
+
+
+class DenseGridOverflow(RuntimeError):
+    """REGTR_STATUS_GRID: redo the pyramid with the sort-based voxel sub-sampling (`build(dense=False)`)."""
+
+
 class Pyramid:
     """Device-resident KPConv pyramid with capacity-shaped buffers.  Level sizes live in
     `offs_all[level]` (int32, device); nothing here requires a host synchronisation."""
@@ -100,10 +109,13 @@ class PreprocessorGPU(nn.Module):
         self.compute_upsamples = compute_upsamples
 
     @torch.no_grad()
-    def build(self, points, offs0, n_clouds: int, caps=None, want64: bool = True, upsamples: bool = None) -> Pyramid:
+    def build(self, points, offs0, n_clouds: int, caps=None, want64: bool = True, upsamples: bool = None,
+              dense: bool = True) -> Pyramid:
         """points (cap0,3) f32 packed clouds, offs0 (n_clouds+1) int32 device offsets.
         caps: per-level row capacities (default: every level as large as level 0).
-        upsamples: compute the `upsamples` lists (default: the module's `compute_upsamples`)."""
+        upsamples: compute the `upsamples` lists (default: the module's `compute_upsamples`).
+        dense: voxel sub-sampling by counting sort over a dense grid (default; sets status bit 4 when a cloud's
+        bounding box exceeds the cell budget) or, dense=False, by the sort-based variant."""
         upsamples = self.compute_upsamples if upsamples is None else upsamples
         levels, _, _ = pyramid_plan(self.cfg)
         device = points.device
@@ -128,7 +140,7 @@ class PreprocessorGPU(nn.Module):
             conv32.append(c32); conv64.append(c64)
             if lvl['strided']:
                 nxt, _ = ops.grid_subsample(cur, offs, n_clouds, lvl['dl'], status, out_cap=caps[li + 1],
-                                            out_offs=offs_all[li + 1])
+                                            out_offs=offs_all[li + 1], dense=dense)
                 p32, p64 = ops.ball_query(nxt, offs_all[li + 1], cur, offs, grid, K, r, want64=want64)
                 nxt_grid = ops.CellGrid(nxt, offs_all[li + 1], n_clouds, 2 * r * _CELL_SLACK, status)
                 u64 = None
@@ -143,6 +155,8 @@ class PreprocessorGPU(nn.Module):
 
     @staticmethod
     def check_status(code: int):
+        if code & 4:
+            raise DenseGridOverflow('a cloud spans more voxels than the dense-grid budget (16 cells per point)')
         if code & 1:
             raise RuntimeError('point coordinates exceed the +-32766-cell key range of the voxel / cell grid')
         if code & 2:
@@ -203,8 +217,12 @@ class PreprocessorGPU(nn.Module):
         device = pts[0].device
         points = torch.cat([p.to(torch.float32) for p in pts], dim=0).contiguous()
         offs0 = ops.make_offsets([int(p.shape[0]) for p in pts], device)
-        pyr = self.build(points, offs0, len(pts), upsamples=False if lazy_upsamples else None)
-        return self.finalize(pyr, lazy_upsamples=lazy_upsamples)
+        up = False if lazy_upsamples else None
+        try:
+            return self.finalize(self.build(points, offs0, len(pts), upsamples=up), lazy_upsamples=lazy_upsamples)
+        except DenseGridOverflow:          # sparse / very large extent: sort-based sub-sampling, same results
+            return self.finalize(self.build(points, offs0, len(pts), upsamples=up, dense=False),
+                                 lazy_upsamples=lazy_upsamples)
 
 
 def _meta_private(meta, device):
@@ -305,7 +323,7 @@ class UnaryBlock(nn.Module):
 
     def fuse(self, x, offs, n_clouds, res=None, final_slope=None, m_dev=None, want_flags=False):
         slope = final_slope if final_slope is not None else (-1.0 if self.no_relu else 0.1)
-        if self.use_bn and self.out_dim % 32 == 0:
+        if self.use_bn and self.out_dim % 32 == 0 and EPILOGUE_STATS:
             # Linear with the InstanceNorm statistics accumulated in the GEMM epilogue, then the apply pass
             y, stats = ops.linear_instats(x, self.mlp.weight, offs, n_clouds, m_dev=m_dev)
             return self.batch_norm.apply(y, stats, offs, n_clouds, res=res, slope=slope, want_flags=want_flags)
@@ -380,7 +398,7 @@ class ResnetBottleneckBlock(nn.Module):
         else:
             x = self.unary1.fuse(features, offs_pre, nc, m_dev=ns_dev) if isinstance(self.unary1, UnaryBlock) \
                 else features
-        if self.use_bn and self.KPConv.out_channels % 32 == 0:
+        if self.use_bn and self.KPConv.out_channels % 32 == 0 and EPILOGUE_STATS:
             x, stats = self.KPConv(q, s, idx, x, nq_dev, ns_dev, row_flags=flags, instats=(offs_post, nc))
             x = self.batch_norm_conv.apply(x, stats, offs_post, nc, slope=0.1)
         else:

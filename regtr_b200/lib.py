@@ -31,11 +31,15 @@ _Z = _c.c_size_t
 SIGNATURES = {
     'regtr_version': (_I, []),
     'regtr_build_info': (_c.c_char_p, []),
-    'regtr_grid_subsample_ws_bytes': (_Z, [_I]),
-    'regtr_grid_subsample': (_I, [_P, _P, _I, _I, _F, _P, _I, _P, _P, _P, _Z, _P]),
+    'regtr_grid_subsample_ws_bytes': (_Z, [_I, _I]),
+    'regtr_grid_subsample_state_bytes': (_Z, [_I]),
+    'regtr_grid_subsample': (_I, [_P, _P, _I, _I, _F, _P, _I, _P, _P, _P, _Z, _P, _Z, _P]),
+    'regtr_grid_subsample_sorted_ws_bytes': (_Z, [_I]),
+    'regtr_grid_subsample_sorted': (_I, [_P, _P, _I, _I, _F, _P, _I, _P, _P, _P, _Z, _P]),
     'regtr_cellgrid_bytes': (_Z, [_I]),
     'regtr_cellgrid_ws_bytes': (_Z, [_I]),
-    'regtr_cellgrid_build': (_I, [_P, _P, _I, _I, _F, _P, _P, _P, _P, _Z, _P]),
+    'regtr_cellgrid_state_bytes': (_Z, [_I]),
+    'regtr_cellgrid_build': (_I, [_P, _P, _I, _I, _F, _P, _P, _P, _P, _Z, _P, _Z, _P]),
     'regtr_ball_query': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P, _P]),
     'regtr_kpconv_ws_bytes': (_Z, [_I, _I, _I]),
     'regtr_kpconv_fwd_ws_bytes': (_Z, [_I, _I, _I, _I]),
@@ -55,11 +59,11 @@ SIGNATURES = {
     'regtr_layernorm_pos': (_I, [_P, _P, _P, _P, _I, _P, _I, _F, _P, _P, _P]),
     'regtr_attention_plan': (_I, [_P, _I, _P, _P]),
     'regtr_corr_decode_fwd': (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
-    'regtr_mha_varlen_fwd': (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    'regtr_mha_varlen_fwd': (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _F, _P]),
     'regtr_gemm_tf32x3_qkv_bf16': (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P]),
     'regtr_mha_bf16_tc_fwd': (_I, [_P, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
     'regtr_gemm_tf32x3_qkv_split': (_I, [_P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _F, _P, _I, _P, _I, _P, _P]),
-    'regtr_mha_tf32_tc_fwd': (_I, [_P, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    'regtr_mha_tf32_tc_fwd': (_I, [_P, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _P]),
     'regtr_kabsch_fwd': (_I, [_P, _P, _P, _P, _I, _P, _P]),
     'regtr_pose_from_corr': (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
     'regtr_status_clear': (_I, [_P, _P]),

@@ -119,22 +119,31 @@ def new_status(device) -> torch.Tensor:
 
 # ---------------------------------------------------------------- pre-processing
 
-def grid_subsample(xyz, offs, n_clouds: int, dl: float, status, out_cap=None, out_offs=None):
+def grid_subsample(xyz, offs, n_clouds: int, dl: float, status, out_cap=None, out_offs=None, dense: bool = True):
     """-> (out_xyz (out_cap,3) capacity buffer, out_offs (n_clouds+1) int32).  No host sync.
     out_cap defaults to the input capacity (always sufficient); a smaller value is memory-safe but
-    raises REGTR_STATUS_CAPACITY in `status` when the sub-sampled level does not fit."""
+    raises REGTR_STATUS_CAPACITY in `status` when the sub-sampled level does not fit.
+    dense=True: counting sort over a dense voxel grid (hand-written kernels; raises REGTR_STATUS_GRID in
+    `status` when a cloud's bounding box exceeds the cell budget); dense=False: sort-based variant (any extent)."""
     L = _lib.load()
     _chk(xyz, torch.float32, 'xyz', 2); _chk(offs, torch.int32, 'offs', 1)
     n_cap = xyz.shape[0]
     out_cap = n_cap if out_cap is None else int(out_cap)
     out_xyz = torch.empty((out_cap, 3), dtype=torch.float32, device=xyz.device)
     out_offs = torch.empty(n_clouds + 1, dtype=torch.int32, device=xyz.device) if out_offs is None else out_offs
-    nb = L.regtr_grid_subsample_ws_bytes(n_cap)
-    ws = workspace(nb, xyz.device)
-    _lib.check(L.regtr_grid_subsample(_p(xyz), _p(offs), n_clouds, n_cap, float(dl), _p(out_xyz), out_cap,
-                                      _p(out_offs), _p(status), _p(ws), ws.numel(), _stream()),
-               'regtr_grid_subsample')
-    _count(4)
+    if dense:
+        ws = workspace(L.regtr_grid_subsample_ws_bytes(n_cap, n_clouds), xyz.device)
+        state = workspace(L.regtr_grid_subsample_state_bytes(n_cap), xyz.device, 'subsample_state', zero=True)
+        _lib.check(L.regtr_grid_subsample(_p(xyz), _p(offs), n_clouds, n_cap, float(dl), _p(out_xyz), out_cap,
+                                          _p(out_offs), _p(status), _p(ws), ws.numel(), _p(state), state.numel(),
+                                          _stream()), 'regtr_grid_subsample')
+        _count(7)
+    else:
+        ws = workspace(L.regtr_grid_subsample_sorted_ws_bytes(n_cap), xyz.device)
+        _lib.check(L.regtr_grid_subsample_sorted(_p(xyz), _p(offs), n_clouds, n_cap, float(dl), _p(out_xyz), out_cap,
+                                                 _p(out_offs), _p(status), _p(ws), ws.numel(), _stream()),
+                   'regtr_grid_subsample_sorted')
+        _count(4)
     return out_xyz, out_offs
 
 
@@ -150,9 +159,10 @@ class CellGrid:
         self.buf = torch.empty(L.regtr_cellgrid_bytes(self.n_cap), dtype=torch.uint8, device=xyz.device)
         self.order = torch.empty(max(self.n_cap, 1), dtype=torch.int32, device=xyz.device)
         ws = workspace(L.regtr_cellgrid_ws_bytes(self.n_cap), xyz.device)
+        state = workspace(L.regtr_cellgrid_state_bytes(self.n_cap), xyz.device, 'scan_state', zero=True)
         _lib.check(L.regtr_cellgrid_build(_p(xyz), _p(offs), n_clouds, self.n_cap, self.cell, _p(self.buf),
-                                          _p(self.order), _p(status), _p(ws), ws.numel(), _stream()),
-                   'regtr_cellgrid_build')
+                                          _p(self.order), _p(status), _p(ws), ws.numel(), _p(state), state.numel(),
+                                          _stream()), 'regtr_cellgrid_build')
         _count(4)
 
 
@@ -430,10 +440,11 @@ def layernorm_pos(x, gamma, beta, pos=None, eps: float = 1e-5, want_plain=True, 
 
 
 def attention_plan(offs, B: int):
-    """Device-side (4, 2B) int32 table: q_start, q_len, cross k_start, cross k_len.  No host sync."""
+    """Device-side (6, 2B + 1) int32 table: q_start, q_len, cross k_start, cross k_len, then the exclusive prefixes
+    of the 64- and 128-query tile counts per problem (entry 2B = total).  No host sync."""
     L = _lib.load()
     _chk(offs, torch.int32, 'offs', 1)
-    plan = torch.empty((4, 2 * B), dtype=torch.int32, device=offs.device)
+    plan = torch.empty((6, 2 * B + 1), dtype=torch.int32, device=offs.device)
     _lib.check(L.regtr_attention_plan(_p(offs), B, _p(plan), _stream()), 'regtr_attention_plan')
     _count(1)
     return plan
@@ -456,7 +467,7 @@ def corr_decode(qp, kp, xyz, q_start, q_len, k_start, k_len, max_q_len: int, n_l
     return out
 
 
-def mha_varlen(q, k, v, q_start, q_len, k_start, k_len, max_q_len: int, n_heads: int, out=None):
+def mha_varlen(q, k, v, q_start, q_len, k_start, k_len, max_q_len: int, n_heads: int, out=None, tiles=None):
     """softmax(q k^T / sqrt(dh)) v per head over explicit (query range, key range) problems.
     q/k/v may be column slices of a wider row-major matrix (stride(0) is the leading dim)."""
     L = _lib.load()
@@ -470,11 +481,12 @@ def mha_varlen(q, k, v, q_start, q_len, k_start, k_len, max_q_len: int, n_heads:
     if TRACE is not None:
         ql, kl = q_len.tolist(), k_len.tolist()
         TRACE.append(('mha', dict(pairs_qk=sum(a * b for a, b in zip(ql, kl)), E=E, tokens=sum(ql)),
-                      lambda: mha_varlen(q, k, v, q_start, q_len, k_start, k_len, max_q_len, n_heads, out=out)))
+                      lambda: mha_varlen(q, k, v, q_start, q_len, k_start, k_len, max_q_len, n_heads, out=out, tiles=tiles)))
+    tb, mt = (tiles[0], int(tiles[1])) if tiles is not None else (None, 0)     # (device tile table, host bound)
     _lib.check(L.regtr_mha_varlen_fwd(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out),
                                       out.stride(0), _p(q_start), _p(q_len), _p(k_start), _p(k_len),
-                                      q_start.numel(), int(max_q_len), n_heads, dh, 1.0 / math.sqrt(dh), _stream()),
-               'regtr_mha_varlen_fwd')
+                                      q_start.numel(), int(max_q_len), _p(tb), mt, n_heads, dh, 1.0 / math.sqrt(dh),
+                                      _stream()), 'regtr_mha_varlen_fwd')
     _count(1)
     return out
 
@@ -501,7 +513,7 @@ def mha_bf16_tc(x, in_w, in_b, q_start, q_len, k_start, k_len, max_q_len: int, n
     return out
 
 
-def mha_tf32_tc(x, in_w, in_b, q_start, q_len, k_start, k_len, max_q_len: int, n_heads: int, m_dev=None):
+def mha_tf32_tc(x, in_w, in_b, q_start, q_len, k_start, k_len, max_q_len: int, n_heads: int, m_dev=None, tiles=None):
     """Attention block core, fp32-accurate, on the tcgen05 tensor cores: packed in-projection (3xTF32 GEMM whose
     epilogue writes q / k / v^T as TF32 (hi, lo) halves) + the TMA-fed 3xTF32 attention kernel (P in tensor memory).
     x (N,E) fp32 (already LN + pos); returns O (N,E) fp32."""
@@ -518,6 +530,7 @@ def mha_tf32_tc(x, in_w, in_b, q_start, q_len, k_start, k_len, max_q_len: int, n
                                              float(qscale), _p(qk4), 4 * E, _p(vt2), ld_vt, _p(m_dev), _stream()),
                'regtr_gemm_tf32x3_qkv_split')
     out = torch.empty((N, E), dtype=torch.float32, device=x.device)
+    tb, mt = (tiles[0], int(tiles[1])) if tiles is not None else (None, 0)
     if TRACE is not None:
         ql, kl = q_len.tolist(), k_len.tolist()
         TRACE.append(('gemm', dict(M=N, N=3 * E, K=E, split_k=False, qkv_split=True), lambda: L.regtr_gemm_tf32x3_qkv_split(
@@ -525,11 +538,11 @@ def mha_tf32_tc(x, in_w, in_b, q_start, q_len, k_start, k_len, max_q_len: int, n
             _p(vt2), ld_vt, _p(m_dev), _stream())))
         TRACE.append(('mha', dict(pairs_qk=sum(a * b for a, b in zip(ql, kl)), E=E, tokens=sum(ql)),
                       lambda: L.regtr_mha_tf32_tc_fwd(_p(qk4), 4 * E, _p(vt2), ld_vt, N, _p(out), E, _p(q_start), _p(q_len),
-                                                      _p(k_start), _p(k_len), q_start.numel(), int(max_q_len), n_heads, dh,
-                                                      _stream())))
+                                                      _p(k_start), _p(k_len), q_start.numel(), int(max_q_len), _p(tb), mt,
+                                                      n_heads, dh, _stream())))
     _lib.check(L.regtr_mha_tf32_tc_fwd(_p(qk4), 4 * E, _p(vt2), ld_vt, N, _p(out), E, _p(q_start), _p(q_len),
-                                       _p(k_start), _p(k_len), q_start.numel(), int(max_q_len), n_heads, dh, _stream()),
-               'regtr_mha_tf32_tc_fwd')
+                                       _p(k_start), _p(k_len), q_start.numel(), int(max_q_len), _p(tb), mt, n_heads, dh,
+                                       _stream()), 'regtr_mha_tf32_tc_fwd')
     _count(2)
     return out
 

@@ -232,6 +232,7 @@ class GraphedRegTR:
         self.ratio, self.retry_ratio = ratio, retry_ratio   # level-to-level capacity ratio (real data: 0.19-0.27)
         self.stages = stages
         self.ratios = {}
+        self.sparse = set()             # buckets whose clouds overflowed the dense voxel grid: captured sort-based
         self.graphs = {}
         self.fallbacks = 0
         self.wait_s = 0.0               # host time spent blocked in result() waiting for the GPU (diagnostics)
@@ -267,7 +268,8 @@ class GraphedRegTR:
 
         def s_pre():
             box['pyr'] = model.preprocessor.build(st['points'], st['offs0'], 2 * B, caps=caps,
-                                                  want64=self.full_meta, upsamples=False)
+                                                  want64=self.full_meta, upsamples=False,
+                                                  dense=(B, cap0) not in self.sparse)
             box['plan'] = AttentionPlan.from_device(box['pyr'].offs_all[-1], B, caps[-1])
             box['meta'] = box['pyr'].private(static=True)
 
@@ -388,9 +390,12 @@ class GraphedRegTR:
         n_lvl = len(pyr.levels)
         n_meta = st['n_meta']
         code = int(st['tail_np'][n_meta - 1])
-        if code & 2:                            # a level overflowed its capacity: redo eagerly and
-            self.fallbacks += 1                 # re-capture this bucket with more head-room next time
-            if self.ratios.get(key, self.ratio) < self.retry_ratio:
+        if code & 6:                            # a level overflowed its capacity (2) or the dense voxel grid (4):
+            self.fallbacks += 1                 # redo eagerly and re-capture this bucket differently next time
+            if code & 4 and key not in self.sparse:
+                self.sparse.add(key)
+                self._drop(key)
+            elif code & 2 and self.ratios.get(key, self.ratio) < self.retry_ratio:
                 self.ratios[key] = self.retry_ratio
                 self._drop(key)
             dev = model.device                  # the eager forward has no host path: move host clouds first

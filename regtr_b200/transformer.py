@@ -96,26 +96,39 @@ class AttentionPlan:
     `n_dev` (static-shape pipelines only) is the device-side total token count, so that the dense
     layers skip the capacity padding rows."""
 
-    def __init__(self, lens=None, device=None, table=None, max_len=None, n_dev=None):
+    def __init__(self, lens=None, device=None, table=None, max_len=None, n_dev=None, max_tiles=None):
         if table is None:
             n2 = len(lens)
             B = n2 // 2
+            lens = list(map(int, lens))
             starts = [0]
             for v in lens:
-                starts.append(starts[-1] + int(v))
+                starts.append(starts[-1] + v)
             other = [B + c if c < B else c - B for c in range(n2)]
-            rows = [starts[:n2], list(map(int, lens)),                          # query ranges
-                    [starts[o] for o in other], [int(lens[o]) for o in other]]  # cross key ranges
+            t64, t128 = [0], [0]
+            for v in lens:
+                t64.append(t64[-1] + (v + 63) // 64); t128.append(t128[-1] + (v + 127) // 128)
+            rows = [starts[:n2] + [0], lens + [0],                                    # query ranges
+                    [starts[o] for o in other] + [0], [lens[o] for o in other] + [0],  # cross key ranges
+                    t64, t128]                                                        # tile prefixes (total last)
             table = torch.tensor(rows, dtype=torch.int32).to(device)
-            max_len = max(map(int, lens)) if n2 else 0
-        self.q_start, self.q_len, self.xk_start, self.xk_len = table[0], table[1], table[2], table[3]
+            max_len = max(lens) if n2 else 0
+            max_tiles = (t64[-1], t128[-1])
+        n2 = table.shape[1] - 1
+        self.q_start, self.q_len = table[0, :n2], table[1, :n2]
+        self.xk_start, self.xk_len = table[2, :n2], table[3, :n2]
         self.max_len = int(max_len)
         self.n_dev = n_dev
+        # (device tile table, host bound of the total) for the 64-query (mma.sync) and 128-query (tcgen05) cores
+        self.tiles64 = (table[4], int(max_tiles[0]))
+        self.tiles128 = (table[5], int(max_tiles[1]))
 
     @classmethod
     def from_device(cls, offs, B: int, max_len: int):
         """Sync-free construction from device offsets (static-shape / CUDA-graph pipelines)."""
-        return cls(table=ops.attention_plan(offs, B), max_len=max_len, n_dev=offs[2 * B:2 * B + 1])
+        n2 = 2 * B                          # sum_p ceil(len_p / T) <= capacity / T + number of problems
+        return cls(table=ops.attention_plan(offs, B), max_len=max_len, n_dev=offs[2 * B:2 * B + 1],
+                   max_tiles=(max_len // 64 + n2, max_len // 128 + n2))
 
 
 class TransformerCrossEncoderLayer(nn.Module):
@@ -155,7 +168,7 @@ class TransformerCrossEncoderLayer(nn.Module):
         if self.attention_impl == 'tf32_tc' and val_has_pos:
             # parity mode on the Blackwell path: split-epilogue in-projection + TMA-fed tcgen05 3xTF32 attention core
             return ops.mha_tf32_tc(x2p, W, b, plan.q_start, plan.q_len, ks, kl, plan.max_len, self.nhead,
-                                   m_dev=plan.n_dev)
+                                   m_dev=plan.n_dev, tiles=plan.tiles128)
         nd = plan.n_dev
         if val_has_pos:
             qkv = ops.linear(x2p, W, b, m_dev=nd)         # one packed in-projection GEMM
@@ -164,7 +177,7 @@ class TransformerCrossEncoderLayer(nn.Module):
             qk = ops.linear(x2p, W[:2 * E], b[:2 * E], m_dev=nd)
             q, k = qk[:, :E], qk[:, E:]
             v = ops.linear(x2, W[2 * E:], b[2 * E:], m_dev=nd)
-        o = ops.mha_varlen(q, k, v, plan.q_start, plan.q_len, ks, kl, plan.max_len, self.nhead)
+        o = ops.mha_varlen(q, k, v, plan.q_start, plan.q_len, ks, kl, plan.max_len, self.nhead, tiles=plan.tiles64)
         return o
 
     def forward_packed(self, x, pos, plan: AttentionPlan):

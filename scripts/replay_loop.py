@@ -1,6 +1,6 @@
 """A few graph replays of the bench workload (for ncu launch lists / profiles).
 
-    python scripts/replay_loop.py [n_rep] [pairs_per_step] [config]
+    python scripts/replay_loop.py [n_rep] [pairs_per_step] [config] [attention_impl]
 """
 import os
 import sys
@@ -18,6 +18,8 @@ n_rep = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 config = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 cfg = get_config('3dmatch')
+if len(sys.argv) > 4:
+    cfg.attention_impl = sys.argv[4]
 model = RegTR(cfg).to(DEV).eval()
 model.load_state_dict(random_state_dict(cfg, 2024), strict=True)
 runner = GraphedRegTR(model)

@@ -282,6 +282,17 @@ def test_attention_cores_agree_and_match_float64(monkeypatch):
             monkeypatch.setenv('REGTR_MHA_IMPL', impl)
             got = N(ops.mha_varlen(q, k, v, plan.q_start, plan.q_len, ks, kl, plan.max_len, H))
             assert np.abs(got - ref).max() <= 1e-5, (impl, cross)
+            if impl == 'mma':
+                got_mma = got
+        # linear tile table (capacity-shaped launches): host-built exact total, device-built with a capacity bound
+        monkeypatch.setenv('REGTR_MHA_IMPL', 'mma')
+        dplan = AttentionPlan.from_device(ops.make_offsets(lens, DEV), B, n + 500)
+        assert np.array_equal(N(dplan.tiles64[0]), N(plan.tiles64[0])) and dplan.tiles64[1] >= plan.tiles64[1]
+        assert np.array_equal(N(dplan.tiles128[0]), N(plan.tiles128[0]))
+        for pl in (plan, dplan):
+            ks2, kl2 = (pl.xk_start, pl.xk_len) if cross else (pl.q_start, pl.q_len)
+            lin = N(ops.mha_varlen(q, k, v, pl.q_start, pl.q_len, ks2, kl2, pl.max_len, H, tiles=pl.tiles64))
+            assert np.array_equal(lin, got_mma)
 
 
 def test_corr_decode_vs_float64():
@@ -801,6 +812,11 @@ def test_tf32_tcgen05_attention_block_vs_float64(lens):
         got = N(ops.mha_tf32_tc(G(x), G(W), G(b), plan.q_start, plan.q_len, ks, kl, plan.max_len, H))
         assert np.isfinite(got).all()
         assert np.abs(got - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max()), (cross, np.abs(got - ref).max())
+        dplan = AttentionPlan.from_device(ops.make_offsets(lens, DEV), B, n + 300)    # linear 128-query tile table
+        ks2, kl2 = (dplan.xk_start, dplan.xk_len) if cross else (dplan.q_start, dplan.q_len)
+        lin = N(ops.mha_tf32_tc(G(x), G(W), G(b), dplan.q_start, dplan.q_len, ks2, kl2, dplan.max_len, H,
+                                tiles=dplan.tiles128))
+        assert np.array_equal(lin, got)
 
 
 def test_forward_with_tf32_tcgen05_attention_vs_reference_golden():
@@ -821,3 +837,68 @@ def test_forward_with_tf32_tcgen05_attention_vs_reference_golden():
     got = runner(batch)
     assert runner.fallbacks == 0
     assert float((got['pose'] - out['pose']).abs().max()) <= 5e-5
+
+
+# ------------------------------------------------- voxel sub-sampling without a library sort
+
+def test_scan_state_is_clean_across_differently_sized_calls():
+    """The prefix-sum state is laid out per call (tile count): sizes alternate on ONE stream and every call must still
+    equal the oracle -- stale aggregates of a previous layout once aliased counters / flags of the next."""
+    from oracle import pre
+    from regtr_b200 import ops
+    rng = np.random.default_rng(11)
+    cases = [[42000, 40000], [700, 900], [9000, 11000], [38000, 37000], [300], [20000, 100], [42000, 40000]]
+    for lens in cases * 2:
+        n = sum(lens)                                            # extents inside the dense-grid cell budget
+        pts = _pre_inputs(n + int(rng.integers(1, 1000)), lens, scale=0.6 if n < 5000 else (1.0 if n < 30000 else 2.0))
+        offs = ops.make_offsets(lens, DEV)
+        status = ops.new_status(DEV)
+        sub, so = ops.grid_subsample(G(pts), offs, len(lens), 0.05, status)
+        assert int(status.item()) == 0
+        want_sub, want_len = pre.grid_subsample(pts, lens, 0.05)
+        assert np.array_equal(np.diff(N(so)), want_len) and np.array_equal(N(sub)[:int(so[-1])], want_sub)
+        # cell list + radius search over the sub-sampled level (the scan of the cell list has its own state)
+        grid = ops.CellGrid(sub, so, len(lens), 0.125, status)
+        i32, _ = ops.ball_query(sub, so, sub, so, grid, 20, 0.125, want64=False)
+        want_idx = pre.ball_query(want_sub, want_len, want_sub, want_len, 20, 0.125)
+        assert int(status.item()) == 0
+        assert np.array_equal(N(i32)[:len(want_sub)], want_idx)
+
+
+def test_dense_grid_subsample_equals_sorted_variant_and_falls_back_when_sparse():
+    """The dense-grid counting sort (hand-written kernels, own single-pass prefix sum) and the sort-based variant
+    give bit-identical barycentres and offsets; a cloud whose bounding box exceeds the cell budget raises
+    REGTR_STATUS_GRID, and the pre-processor then takes the sort-based path on its own (same result as the oracle)."""
+    from oracle import pre
+    from regtr_b200 import ops
+    from regtr_b200.config import get_config
+    from regtr_b200.kpconv import PreprocessorGPU
+    for lens in ([900, 1100], [1, 2000, 0, 37], [30000, 28000]):
+        pts = _pre_inputs(sum(lens) + 1, lens, scale=0.6 if sum(lens) < 5000 else 1.5)
+        offs = ops.make_offsets(lens, DEV)
+        out = []
+        for dense in (True, True, False):                       # twice dense: the self-cleaning state is reused
+            status = ops.new_status(DEV)
+            sub, so = ops.grid_subsample(G(pts), offs, len(lens), 0.05, status, dense=dense)
+            assert int(status.item()) == 0
+            out.append((N(sub)[:int(so[-1])], N(so)))
+        for a in out[1:]:
+            assert np.array_equal(out[0][0], a[0]) and np.array_equal(out[0][1], a[1])
+        want_sub, want_len = pre.grid_subsample(pts, lens, 0.05)
+        assert np.array_equal(out[0][0], want_sub) and np.array_equal(np.diff(out[0][1]), want_len)
+    # sparse: 3000 points over a 120 m cube at 5 cm voxels -> 1.4e10 cells
+    rng = np.random.default_rng(4)
+    sparse = rng.uniform(-60, 60, size=(3000, 3)).astype(np.float32)
+    status = ops.new_status(DEV)
+    ops.grid_subsample(G(sparse), ops.make_offsets([3000], DEV), 1, 0.05, status)
+    assert int(status.item()) & 4
+    sub2, so2 = ops.grid_subsample(G(pts), offs, len(lens), 0.05, ops.new_status(DEV))      # state still clean afterwards
+    assert np.array_equal(N(sub2)[:int(so2[-1])], out[0][0])
+    cfg = get_config('3dmatch')
+    big = (rng.uniform(-40, 40, size=(4000, 3))).astype(np.float32)
+    big[:2000] = rng.uniform(-1, 1, size=(2000, 3))             # a dense core so that the pyramid is not trivial
+    meta = PreprocessorGPU(cfg)([G(big[:2500]), G(big[2500:])])
+    want = pre.preprocess(cfg, [big[:2500], big[2500:]])
+    for key in ('points', 'neighbors', 'pools', 'stack_lengths'):
+        for lvl, (a, b) in enumerate(zip(meta[key], want[key])):
+            assert np.array_equal(N(a), b), f'{key}[{lvl}]'
