@@ -359,13 +359,32 @@ k_gemm_tf32x3_ts(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 continue;
             }
             if (col0 + 32 <= N && (ldc & 3) == 0 && (!R || (ldr & 3) == 0)) {
+                // through shared memory (the pipeline stages are idle now): the thread-per-row accumulators leave as
+                // 128-byte row segments, 4 rows per warp instruction -- 4 memory wavefronts instead of 32 per store,
+                // and the residual is read the same way
+                float* tile = reinterpret_cast<float*>(base) + q * (32 * 36);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (bias) { const float4 b = *reinterpret_cast<const float4*>(bias + col0 + j); v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w; }
-                    if (rrow) { const float4 rr = *reinterpret_cast<const float4*>(rrow + col0 + j); v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w; }
-                    if (relu) { v[j] = fmaxf(v[j], 0.f); v[j + 1] = fmaxf(v[j + 1], 0.f); v[j + 2] = fmaxf(v[j + 2], 0.f); v[j + 3] = fmaxf(v[j + 3], 0.f); }
-                    if (row_ok) *reinterpret_cast<float4*>(crow + col0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(tile + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                const int cq = lane & 7, rsub = lane >> 3, row_base = m0 + q * 32;
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias) b4 = *reinterpret_cast<const float4*>(bias + col0 + 4 * cq);
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int rr = it * 4 + rsub, rg = row_base + rr;
+                    float4 o = *reinterpret_cast<const float4*>(tile + rr * 36 + 4 * cq);
+                    if (rg < M) {
+                        o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+                        if (R) {
+                            const float4 rv = *reinterpret_cast<const float4*>(R + (size_t)rg * ldr + col0 + 4 * cq);
+                            o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                        }
+                        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        *reinterpret_cast<float4*>(C + (size_t)rg * ldc + col0 + 4 * cq) = o;
+                    }
                 }
+                __syncwarp();                                  // the tile is rewritten by the next 32-column chunk
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -583,6 +602,9 @@ static int gemm_dispatch(const float* A, int lda, const float* B_hi, const float
     // epilogue with the other's MMAs -- also across the independent forwards of the multi-stream executor; only long
     // accumulation runs take the 4-stage variant with two interleaved accumulators.  (Deeper single-CTA-per-SM
     // variants with 3-4 accumulators were measured: 2x more accurate at K = 960, but 1.3-2x slower per launch.)
+    // (4- and 6-stage single-CTA-per-SM variants for launches of <= 148 CTAs were measured too: the serial forward gets
+    // 4 % shorter, the multi-stream throughput 3 % lower -- a CTA that owns the SM's shared memory keeps the other
+    // forwards' CTAs out.)
     if (bn == 128) { if (nkb_split <= 16) REGTR_TS_CASE(128, 1, 2); REGTR_TS_CASE(128, 2, 4); }
     if (bn == 64) REGTR_TS_CASE(64, 2, 3);
     REGTR_TS_CASE(32, 4, 4);

@@ -108,7 +108,7 @@ __global__ void k_cloud_offsets(const unsigned long long* __restrict__ skeys, co
 // by the last tile to finish: the buffer needs to be cleared once, when it is allocated.
 //   MODE 0: in int32 counts -> out int32 exclusive sums
 //   MODE 1: in uint32 counts -> out uint64 { hi = number of NON-ZERO entries before, lo = sum before }
-constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 16, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 struct ScanState {                 // zero-initialised, self-cleaning
     int ticket, done, pad[62];
@@ -121,9 +121,12 @@ __host__ __device__ inline size_t scan_state_bytes(long long n) {
     return 256 + (size_t)tiles * (sizeof(int) + 2 * sizeof(unsigned long long)) + 64;
 }
 
+// n_dev (optional): the number of leading elements that matter is *n_dev + 1 (device-side, <= n): CTAs beyond it
+// only take their ticket and leave -- the voxel grid scans its occupied part of a capacity-sized counter array.
 template <int MODE>
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_lookback(const void* __restrict__ in_, void* __restrict__ out_, int n, ScanState* st, int num_tiles) {
+k_scan_lookback(const void* __restrict__ in_, void* __restrict__ out_, int n, const int* __restrict__ n_dev, ScanState* st,
+                int num_tiles) {
     typedef unsigned long long u64;
     __shared__ u64 s_warp[SCAN_THREADS / 32];
     __shared__ u64 s_excl;
@@ -131,95 +134,127 @@ k_scan_lookback(const void* __restrict__ in_, void* __restrict__ out_, int n, Sc
     int* flags = reinterpret_cast<int*>(reinterpret_cast<char*>(st) + 256);
     u64* aggregate = reinterpret_cast<u64*>(reinterpret_cast<char*>(st) + 256 + (((size_t)num_tiles * sizeof(int) + 15) & ~(size_t)15));
     u64* inclusive = aggregate + num_tiles;
+    if (n_dev) n = min(n, *n_dev + 1);
+    const int live_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (threadIdx.x == 0) s_tile = atomicAdd(&st->ticket, 1);
     __syncthreads();
     const int tile = s_tile;
-    const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    u64 v[SCAN_ITEMS];
-    u64 tsum = 0;
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        u64 x = 0;
-        if (base + j < n) {
-            if (MODE == 0) x = (u64)(unsigned)reinterpret_cast<const int*>(in_)[base + j];
-            else { const unsigned c = reinterpret_cast<const unsigned*>(in_)[base + j]; x = ((u64)(c != 0) << 32) | c; }
-        }
-        v[j] = tsum;                                  // exclusive prefix inside the thread
-        tsum += x;
-    }
-    // block-level exclusive scan of the per-thread sums
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64 incl = tsum;
+    if (tile < live_tiles) {
+        const int base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+        unsigned x[SCAN_ITEMS];
+        if (base + SCAN_ITEMS <= n) {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u64 t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    u64 warp_off = 0, block_total = 0;
-#pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-        if (w < warp) warp_off += s_warp[w];
-        block_total += s_warp[w];
-    }
-    const u64 thread_excl = warp_off + incl - tsum;
-    if (threadIdx.x == 0) {
-        u64 excl = 0;
-        if (tile == 0) {
-            inclusive[0] = block_total;
-            __threadfence();
-            atomicExch(&flags[0], 2);
-        } else {
-            aggregate[tile] = block_total;
-            __threadfence();
-            atomicExch(&flags[tile], 1);
-            for (int pred = tile - 1;; --pred) {
-                int f;
-                unsigned spin = 0;
-                do {                                      // bounded: a corrupted state must trap, not hang the device
-                    f = atomicAdd(&flags[pred], 0);
-                    if (++spin > (1u << 26)) __trap();
-                } while (f == 0);
-                __threadfence();
-                if (f == 2) { excl += *reinterpret_cast<volatile u64*>(&inclusive[pred]); break; }
-                excl += *reinterpret_cast<volatile u64*>(&aggregate[pred]);
+            for (int j = 0; j < SCAN_ITEMS / 4; ++j) {
+                const uint4 q = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned*>(in_) + base)[j];
+                x[4 * j] = q.x; x[4 * j + 1] = q.y; x[4 * j + 2] = q.z; x[4 * j + 3] = q.w;
             }
-            inclusive[tile] = excl + block_total;
-            __threadfence();
-            atomicExch(&flags[tile], 2);
-        }
-        s_excl = excl;
-    }
-    __syncthreads();
-    const u64 off = s_excl + thread_excl;
+        } else {
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        if (base + j < n) {
-            if (MODE == 0) reinterpret_cast<int*>(out_)[base + j] = (int)(unsigned)(off + v[j]);
-            else reinterpret_cast<u64*>(out_)[base + j] = off + v[j];
+            for (int j = 0; j < SCAN_ITEMS; ++j) x[j] = base + j < n ? reinterpret_cast<const unsigned*>(in_)[base + j] : 0u;
+        }
+        u64 v[SCAN_ITEMS];
+        u64 tsum = 0;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) {
+            v[j] = tsum;                                  // exclusive prefix inside the thread
+            tsum += MODE == 0 ? (u64)x[j] : (((u64)(x[j] != 0) << 32) | x[j]);
+        }
+        // block-level exclusive scan of the per-thread sums
+        u64 incl = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        u64 warp_off = 0, block_total = 0;
+#pragma unroll
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+            if (w < warp) warp_off += s_warp[w];
+            block_total += s_warp[w];
+        }
+        const u64 thread_excl = warp_off + incl - tsum;
+        if (warp == 0) {
+            // publish the aggregate, then look back a WARP of predecessors at a time: lane l reads tile - 1 - l
+            // (aggregate or inclusive prefix, whichever is published); the nearest inclusive prefix ends the walk
+            if (lane == 0) {
+                if (tile == 0) { inclusive[0] = block_total; __threadfence(); atomicExch(&flags[0], 2); }
+                else { aggregate[tile] = block_total; __threadfence(); atomicExch(&flags[tile], 1); }
+            }
+            u64 excl = 0;
+            if (tile > 0) {
+                for (int first = tile - 1;; first -= 32) {
+                    const int pred = first - lane;
+                    int f = 2;
+                    u64 val = 0;                          // before tile 0: an inclusive prefix of zero
+                    if (pred >= 0) {
+                        unsigned spin = 0;
+                        do {                              // bounded: a corrupted state must trap, not hang the device
+                            f = atomicAdd(&flags[pred], 0);
+                            if (++spin > (1u << 26)) __trap();
+                        } while (f == 0);
+                        __threadfence();
+                        val = *reinterpret_cast<volatile u64*>(f == 2 ? &inclusive[pred] : &aggregate[pred]);
+                    }
+                    const unsigned done_mask = __ballot_sync(0xffffffffu, f == 2);
+                    const int stop = done_mask ? __ffs(done_mask) - 1 : 31;
+                    u64 part = lane <= stop ? val : 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                    excl += part;
+                    if (done_mask) break;
+                }
+                if (lane == 0) { inclusive[tile] = excl + block_total; __threadfence(); atomicExch(&flags[tile], 2); }
+            }
+            if (lane == 0) s_excl = excl;
+        }
+        __syncthreads();
+        const u64 off = s_excl + thread_excl;
+        if (base + SCAN_ITEMS <= n) {
+            if (MODE == 0) {
+#pragma unroll
+                for (int j = 0; j < SCAN_ITEMS / 4; ++j)
+                    reinterpret_cast<int4*>(reinterpret_cast<int*>(out_) + base)[j] =
+                        make_int4((int)(unsigned)(off + v[4 * j]), (int)(unsigned)(off + v[4 * j + 1]),
+                                  (int)(unsigned)(off + v[4 * j + 2]), (int)(unsigned)(off + v[4 * j + 3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < SCAN_ITEMS / 2; ++j)
+                    reinterpret_cast<ulonglong2*>(reinterpret_cast<u64*>(out_) + base)[j] = make_ulonglong2(off + v[2 * j], off + v[2 * j + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j) {
+                if (base + j < n) {
+                    if (MODE == 0) reinterpret_cast<int*>(out_)[base + j] = (int)(unsigned)(off + v[j]);
+                    else reinterpret_cast<u64*>(out_)[base + j] = off + v[j];
+                }
+            }
         }
     }
-    // the last tile to FINISH restores the zero state (nobody reads flags any more: every tile has its prefix)
+    // the last CTA to FINISH restores the zero state (nobody reads flags any more: every tile has its prefix, and
+    // every launched CTA has taken its ticket)
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        s_tile = atomicAdd(&st->done, 1) == num_tiles - 1;
+        s_tile = atomicAdd(&st->done, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
     if (s_tile) {
         // aggregates and prefixes too: the next call may lay the state out for another tile count, where these
         // words are somebody's flags (or, in the voxel counting sort, cell counters)
-        for (int t = threadIdx.x; t < num_tiles; t += SCAN_THREADS) { flags[t] = 0; aggregate[t] = 0; inclusive[t] = 0; }
+        for (int t = threadIdx.x; t < live_tiles; t += SCAN_THREADS) { flags[t] = 0; aggregate[t] = 0; inclusive[t] = 0; }
         if (threadIdx.x == 0) { st->ticket = 0; st->done = 0; }
     }
 }
 
 template <int MODE>
-static int launch_scan(const void* in, void* out, int n, void* state, cudaStream_t st) {
+static int launch_scan(const void* in, void* out, int n, const int* n_dev, void* state, cudaStream_t st) {
     const int tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (tiles <= 0) return REGTR_OK;
-    k_scan_lookback<MODE><<<tiles, SCAN_THREADS, 0, st>>>(in, out, n, reinterpret_cast<ScanState*>(state), tiles);
+    k_scan_lookback<MODE><<<tiles, SCAN_THREADS, 0, st>>>(in, out, n, n_dev, reinterpret_cast<ScanState*>(state), tiles);
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
 }
@@ -661,7 +696,7 @@ int regtr_grid_subsample(const float* xyz, const int32_t* offs, int n_clouds, in
     REGTR_CHECK_LAUNCH();
     k_vox_count<<<regtr_cdiv(n_cap, T), T, 0, st>>>(xyz, offs, n_clouds, n_cap, dl, w.lay, cells_cap, cnt, w.cell_of, status);
     REGTR_CHECK_LAUNCH();
-    const int rc = launch_scan<1>(cnt, w.pre, (int)cells_cap + 1, scan_state, st);
+    const int rc = launch_scan<1>(cnt, w.pre, (int)cells_cap + 1, w.total, scan_state, st);
     if (rc != REGTR_OK) return rc;
     k_vox_scatter<<<regtr_cdiv(n_cap, T), T, 0, st>>>(n_cap, w.cell_of, w.pre, cnt, w.members);
     REGTR_CHECK_LAUNCH();
@@ -779,7 +814,7 @@ int regtr_cellgrid_build(const float* xyz, const int32_t* offs, int n_clouds, in
     k_cell_count<<<regtr_cdiv(n_cap, T), T, 0, st>>>(xyz, offs, n_clouds, n_cap, cell, w.tkeys, w.cnt, log2t, w.slot_of,
                                                      status, hdr);
     REGTR_CHECK_LAUNCH();
-    const int rc = launch_scan<0>(w.cnt, w.start, t_size, state, st);
+    const int rc = launch_scan<0>(w.cnt, w.start, t_size, nullptr, state, st);
     if (rc != REGTR_OK) return rc;
     k_cell_scatter<<<regtr_cdiv(n_cap, T), T, 0, st>>>(xyz, offs, n_clouds, n_cap, w.slot_of, w.start, w.cursor, sxyzi,
                                                        order);
