@@ -232,13 +232,16 @@ def peak_table():
                     source='fallback (B200_PROFILING.md: 6.65 TB/s, 1.59 PFLOP/s)')
 
 
-def ncu_traffic(kernel_key):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel family, read at run time from the
-    committed ncu summary (profiles/r02_ncu_traffic.json, written by scripts/ncu_summary.py from one
-    `ncu --set full` capture of this workload); None when no capture of this build is committed."""
+def ncu_traffic(kernel_key, pairs):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel family (for `whole_forward`: per replay),
+    read at run time from the committed ncu summary (profiles/r02_ncu_traffic.json, written by
+    scripts/ncu_summary.py from one `ncu --set full` capture of a graph replay of this workload at the same number of
+    pairs per forward); None when no capture at this batch size is committed.  kpconv_gather: the aggregation kernels
+    only -- the [Nq, 15 Cin] intermediate they write is read back by the contraction GEMM, which the capture lists
+    under gemm_tf32x3."""
     try:
         d = json.load(open(os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')))
-        return d.get(kernel_key)
+        return d[str(pairs)][kernel_key]['dram_bytes_per_launch']
     except Exception:
         return None
 
@@ -319,7 +322,7 @@ def measure_rooflines(model, batch_at, resident, flush, W, K, B, ms_per_step):
                   kernel='KPConv neighbour gather + kernel-point influence + aggregation (one launch per KPConv, each '
                          'timed alone right after an L2 flush); bytes = SURVEY 8d algorithmic bytes of the KPConv op',
                   achieved=ach, peak=pk['hbm_gbs'], unit='GB/s', frac=ach / pk['hbm_gbs'],
-                  traffic=ncu_traffic('kpconv_gather'), traffic_unit='bytes/launch (committed ncu capture)',
+                  traffic=ncu_traffic('kpconv_gather', B), traffic_unit='bytes/launch (committed ncu capture)',
                   peak_source=pk['source'], launches=len(ktr), algorithmic_bytes_per_step=step_bytes,
                   algorithmic_bytes_per_launch=step_bytes / max(len(ktr), 1), ms_per_step=gather_ms,
                   ms_per_step_l2_warm=warm_ms, frac_l2_warm=step_bytes / (warm_ms * 1e-3) / 1e9 / pk['hbm_gbs'],
@@ -344,7 +347,7 @@ def measure_rooflines(model, batch_at, resident, flush, W, K, B, ms_per_step):
                 kernel='k_gemm_tf32x3 (+ split-K reduce): every nn.Linear and the KPConv weight contraction; flops = '
                        '2*M*N*K*3 TF32 MMA flops (3xTF32 split) summed over the launches of one forward, each timed alone '
                        'after an L2 flush',
-                achieved=ach, peak=tf32_peak, unit='TFLOP/s', frac=ach / tf32_peak, traffic=ncu_traffic('gemm_tf32x3'),
+                achieved=ach, peak=tf32_peak, unit='TFLOP/s', frac=ach / tf32_peak, traffic=ncu_traffic('gemm_tf32x3', B),
                 peak_source=pk['source'] + ': bf16_tflops / 2 (dense TF32)', launches=n_gemm, ms_per_step=g_ms,
                 fp32_equiv_flops_per_step=g_flops, fp32_equiv_tflops=g_flops / (g_ms * 1e-3) / 1e12,
                 top_shapes=[dict(M=k[0], N=k[1], K=k[2], launches=c[0], us=round(c[1] * 1e3, 1),
@@ -365,7 +368,7 @@ def measure_rooflines(model, batch_at, resident, flush, W, K, B, ms_per_step):
         att = dict(name='attention_core', bound='tensor',
                    kernel='attention core (softmax(QK^T)V per head, varlen problems): 4*q*k*E flops per problem, x3 '
                           '(3xTF32 split), self and cross launches of the 6 layers',
-                   achieved=ach, peak=tf32_peak, unit='TFLOP/s', frac=ach / tf32_peak, traffic=ncu_traffic('attention_core'),
+                   achieved=ach, peak=tf32_peak, unit='TFLOP/s', frac=ach / tf32_peak, traffic=ncu_traffic('attention_core', B),
                    peak_source=pk['source'] + ': bf16_tflops / 2 (dense TF32)', launches=n_att, ms_per_step=a_ms,
                    fp32_equiv_flops_per_step=a_flops)
 
@@ -377,7 +380,8 @@ def measure_rooflines(model, batch_at, resident, flush, W, K, B, ms_per_step):
                  kernel='whole forward at the benchmarked throughput: fp32-equivalent algorithmic flops of one step '
                         '(dense layers + attention core + KPConv aggregation/influence) / ms_per_step; the fp32-accurate '
                         'path issues 3 TF32 MMA flops per algorithmic flop',
-                 achieved=3.0 * tf, peak=sus, unit='TFLOP/s', frac=3.0 * tf / sus, traffic=None,
+                 achieved=3.0 * tf, peak=sus, unit='TFLOP/s', frac=3.0 * tf / sus, traffic=ncu_traffic('whole_forward', B),
+                 traffic_unit='DRAM bytes of one forward (all kernels of a graph replay, committed ncu capture)',
                  peak_source=pk['source'] + ': bf16_tflops_sustained / 2 (dense TF32, kernel inside a long step)',
                  fp32_equiv_flops_per_step=total_flops, fp32_equiv_tflops=tf,
                  hbm_algorithmic_bytes_per_step=step_bytes,
