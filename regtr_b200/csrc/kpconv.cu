@@ -365,7 +365,10 @@ struct AggItem {            // registers that travel with an item through the lo
     int f0, f1;             // "row sums to > 0" flags of the two neighbours
 };
 
-__global__ void __launch_bounds__(PIPE_WARPS * 32, 4)
+// NH: 32-channel halves per work item.  NH = 2 (Cin % 64 == 0) shares the index / coordinate / influence work of a
+// query between two channel halves: 65 instead of 92 issue slots per (8 neighbours, 32 channels) in the main loop.
+template <int NH>
+__global__ void __launch_bounds__(PIPE_WARPS * 32, NH == 1 ? 4 : 2)
 k_kpconv_agg_pipe(const float* __restrict__ q, const float* __restrict__ s, const int32_t* __restrict__ idx,
                   const float* __restrict__ x, const uint8_t* __restrict__ flags, const float* __restrict__ kp,
                   int Nq, int Ns, const int32_t* __restrict__ nq_dev, const int32_t* __restrict__ ns_dev, int K, int Cin,
@@ -373,8 +376,8 @@ k_kpconv_agg_pipe(const float* __restrict__ q, const float* __restrict__ s, cons
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Kp = (K + 7) & ~7;
-    constexpr int ROW = 32;
-    // per warp, two buffers of: rows[Kp][32] (16-byte chunks swizzled) | rel[Kp] (float4) | id[Kp]
+    constexpr int ROW = 32 * NH;
+    // per warp, two buffers of: rows[Kp][32 NH] (16-byte chunks swizzled per 128-byte group) | rel[Kp] (float4) | id[Kp]
     const int buf_floats = Kp * (ROW + 5);
     float* wbase = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 2 * buf_floats;
     if (ns_dev) Ns = min(Ns, *ns_dev);
@@ -440,10 +443,11 @@ k_kpconv_agg_pipe(const float* __restrict__ q, const float* __restrict__ s, cons
         if (lane < padded - base) { id_s[base + lane] = 0; rel_s[base + lane] = make_float4(1e6f, 1e6f, 1e6f, 0.f); }
         __syncwarp();
         if (it < n_items) {
-            const int c = lane & 7, rg = lane >> 3;                  // 8 16-byte chunks per row, 4 rows per instruction
-            const float* xs = x + (size_t)((int)it & slice_mask) * 32 + 4 * c;
-            uint32_t dst = (uint32_t)__cvta_generic_to_shared(rows_s) + (uint32_t)(rg * ROW) * 4u;
-            for (int n = rg; n < padded; n += 4, dst += 4 * ROW * 4) {
+            constexpr int CPR = 8 * NH, RPI = 32 / CPR;              // 16-byte chunks per row, rows per warp instruction
+            const int c = lane % CPR, rg = lane / CPR;
+            const float* xs = x + (size_t)((int)it & slice_mask) * ROW + 4 * c;
+            uint32_t dst = (uint32_t)__cvta_generic_to_shared(rows_s) + (uint32_t)(rg * ROW + (c & ~7) * 4) * 4u;
+            for (int n = rg; n < padded; n += RPI, dst += RPI * ROW * 4) {
                 const float* src = xs + (size_t)id_s[n] * Cin;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(((c + 2 * n) & 7) * 16)), "l"(src) : "memory");
             }
@@ -474,43 +478,55 @@ k_kpconv_agg_pipe(const float* __restrict__ q, const float* __restrict__ s, cons
         __syncwarp();
         const float* rows_s = wbase + b * buf_floats;
         const float4* rel_s = reinterpret_cast<const float4*>(rows_s + Kp * ROW);
-        float acc[4][4];
+        float acc[NH][4][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int h = 0; h < NH; ++h)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[h][j][e] = 0.f;
         for (int k0 = 0; k0 < pad_cur; k0 += 8) {
             const int n0 = k0 + t, n1 = n0 + 4;        // n0 & 3 == n1 & 3 == t
-            const float4 v0 = *reinterpret_cast<const float4*>(rows_s + n0 * ROW + 4 * ((g + 2 * t) & 7));
-            const float4 v1 = *reinterpret_cast<const float4*>(rows_s + n1 * ROW + 4 * ((g + 2 * t) & 7));
+            const float* row0 = rows_s + n0 * ROW + 4 * ((g + 2 * t) & 7);
+            const float* row1 = rows_s + n1 * ROW + 4 * ((g + 2 * t) & 7);
+            float4 v0[NH], v1[NH];
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                v0[h] = *reinterpret_cast<const float4*>(row0 + 32 * h);
+                v1[h] = *reinterpret_cast<const float4*>(row1 + 32 * h);
+            }
             const float4 r0 = rel_s[n0], r1 = rel_s[n1];
             const float hw[4] = {influence(r0, ax, ay, az, inv_extent), influence(r0, bx, by, bz, inv_extent),
                                  influence(r1, ax, ay, az, inv_extent), influence(r1, bx, by, bz, inv_extent)};
             uint32_t a_hi[4], a_lo[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) { a_hi[e] = tf32_head(hw[e]); a_lo[e] = __float_as_uint(hw[e] - __uint_as_float(a_hi[e])); }
-            const float b0f[4] = {v0.x, v0.y, v0.z, v0.w};
-            const float b1f[4] = {v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t h0 = tf32_head(b0f[j]), h1 = tf32_head(b1f[j]);
-                const uint32_t l0 = __float_as_uint(b0f[j] - __uint_as_float(h0));
-                const uint32_t l1 = __float_as_uint(b1f[j] - __uint_as_float(h1));
-                mma_tf32_16x8x8(acc[j], a_lo, h0, h1);
-                mma_tf32_16x8x8(acc[j], a_hi, l0, l1);
-                mma_tf32_16x8x8(acc[j], a_hi, h0, h1);
+            for (int h = 0; h < NH; ++h) {
+                const float b0f[4] = {v0[h].x, v0[h].y, v0[h].z, v0[h].w};
+                const float b1f[4] = {v1[h].x, v1[h].y, v1[h].z, v1[h].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t h0 = tf32_head(b0f[j]), h1 = tf32_head(b1f[j]);
+                    const uint32_t l0 = __float_as_uint(b0f[j] - __uint_as_float(h0));
+                    const uint32_t l1 = __float_as_uint(b1f[j] - __uint_as_float(h1));
+                    mma_tf32_16x8x8(acc[h][j], a_lo, h0, h1);
+                    mma_tf32_16x8x8(acc[h][j], a_hi, l0, l1);
+                    mma_tf32_16x8x8(acc[h][j], a_hi, h0, h1);
+                }
             }
         }
         float inv;                                    // 1 / max(count, 1): one MUFU (<= 1 ulp)
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"((float)max(cnt_cur, 1)));
-        {
-            float* o = wf + (size_t)(it >> log2_slices) * (KP * Cin) + ((int)it & slice_mask) * 32 + g * Cin + 8 * t;
-            reinterpret_cast<float4*>(o)[0] = make_float4(acc[0][0] * inv, acc[1][0] * inv, acc[2][0] * inv, acc[3][0] * inv);
-            reinterpret_cast<float4*>(o)[1] = make_float4(acc[0][1] * inv, acc[1][1] * inv, acc[2][1] * inv, acc[3][1] * inv);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            float* o = wf + (size_t)(it >> log2_slices) * (KP * Cin) + ((int)it & slice_mask) * ROW + g * Cin + 32 * h + 8 * t;
+            reinterpret_cast<float4*>(o)[0] = make_float4(acc[h][0][0] * inv, acc[h][1][0] * inv, acc[h][2][0] * inv, acc[h][3][0] * inv);
+            reinterpret_cast<float4*>(o)[1] = make_float4(acc[h][0][1] * inv, acc[h][1][1] * inv, acc[h][2][1] * inv, acc[h][3][1] * inv);
             if (row_b) {
                 float* o2 = o + 8 * Cin;
-                reinterpret_cast<float4*>(o2)[0] = make_float4(acc[0][2] * inv, acc[1][2] * inv, acc[2][2] * inv, acc[3][2] * inv);
-                reinterpret_cast<float4*>(o2)[1] = make_float4(acc[0][3] * inv, acc[1][3] * inv, acc[2][3] * inv, acc[3][3] * inv);
+                reinterpret_cast<float4*>(o2)[0] = make_float4(acc[h][0][2] * inv, acc[h][1][2] * inv, acc[h][2][2] * inv, acc[h][3][2] * inv);
+                reinterpret_cast<float4*>(o2)[1] = make_float4(acc[h][0][3] * inv, acc[h][1][3] * inv, acc[h][2][3] * inv, acc[h][3][3] * inv);
             }
         }
         __syncwarp();                                 // all lanes are done with buffer b before it is refilled
@@ -802,23 +818,32 @@ int regtr_kpconv_aggregate(const float* q, const float* s, const int32_t* idx, c
     }
     {   // default: software-pipelined persistent kernel (REGTR_AGG_IMPL=mma / ffma select the older kernels for A/B)
         const char* e = getenv("REGTR_AGG_IMPL");
-        const int S = Cin / 32;
-        if (!e && K <= 64 && (S & (S - 1)) == 0) {
+        const int nh = (Cin % 64 == 0) ? 2 : 1;
+        const int S = Cin / (32 * nh);
+        if (!e && K <= 64 && Cin % 32 == 0 && (S & (S - 1)) == 0) {
             const int Kp = (K + 7) & ~7;
-            const size_t smem = (size_t)PIPE_WARPS * 2 * Kp * (32 + 5) * sizeof(float);
-            static size_t attr_smem = 0;
-            if (smem > 48 * 1024 && smem > attr_smem) {
-                if (cudaFuncSetAttribute(k_kpconv_agg_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-                    return REGTR_ERR_UNSUPPORTED;
-                attr_smem = smem;
+            const size_t smem = (size_t)PIPE_WARPS * 2 * Kp * (32 * nh + 5) * sizeof(float);
+            if (smem > 200 * 1024) return REGTR_ERR_UNSUPPORTED;
+            static size_t attr_smem[2] = {0, 0};
+            if (smem > 48 * 1024 && smem > attr_smem[nh - 1]) {
+                const cudaError_t ea = nh == 1
+                    ? cudaFuncSetAttribute(k_kpconv_agg_pipe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                    : cudaFuncSetAttribute(k_kpconv_agg_pipe<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (ea != cudaSuccess) return REGTR_ERR_UNSUPPORTED;
+                attr_smem[nh - 1] = smem;
             }
             int log2s = 0;
             while ((1 << log2s) < S) ++log2s;
             const long long items = (long long)Nq * S;
-            const int per_sm = smem <= 56 * 1024 ? 4 : (smem <= 75 * 1024 ? 3 : 2);
+            const int fit = (int)((220 * 1024) / (smem + 1024));
+            const int per_sm = std::max(1, std::min(nh == 1 ? 4 : 2, fit));
             const int grid = (int)std::min<long long>((long long)REGTR_NUM_SMS * per_sm, (items + PIPE_WARPS - 1) / PIPE_WARPS);
-            k_kpconv_agg_pipe<<<grid, PIPE_WARPS * 32, smem, st>>>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K, Cin,
-                                                                  log2s, 1.f / extent, wf);
+            if (nh == 1)
+                k_kpconv_agg_pipe<1><<<grid, PIPE_WARPS * 32, smem, st>>>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K,
+                                                                         Cin, log2s, 1.f / extent, wf);
+            else
+                k_kpconv_agg_pipe<2><<<grid, PIPE_WARPS * 32, smem, st>>>(q, s, idx, x, rowflag_ws, kp, Nq, Ns, nq_dev, ns_dev, K,
+                                                                         Cin, log2s, 1.f / extent, wf);
             REGTR_CHECK_LAUNCH();
             return REGTR_OK;
         }

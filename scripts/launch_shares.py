@@ -36,7 +36,7 @@ def short(n):
 names = [short(v['name']) for v in launches.values()]
 vals = list(launches.values())
 n = len(names)
-period = next(p for p in range(50, n // 2 + 1) if names[n - p:] == names[n - 2 * p:n - p])   # replays repeat exactly
+period = next((p for p in range(50, n // 2 + 1) if names[n - p:] == names[n - 2 * p:n - p]), n)   # replays repeat exactly; a trimmed list holds one
 agg = defaultdict(lambda: [0.0, 0, 0.0])
 has_act = False
 for nm, v in zip(names[n - period:], vals[n - period:]):
