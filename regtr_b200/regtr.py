@@ -236,7 +236,22 @@ class GraphedRegTR:
         self.graphs = {}
         self.fallbacks = 0
         self.wait_s = 0.0               # host time spent blocked in result() waiting for the GPU (diagnostics)
+        # the graphs bake in pointers to the split (hi, lo) weights: load_state_dict bumps the model's epoch and
+        # every graph is re-captured on its next use; in-place edits of a parameter need invalidate()
+        self._epoch = getattr(model, '_weights_epoch', 0)
+        if not hasattr(model, '_weights_epoch'):
+            model._weights_epoch = 0
+            model.register_load_state_dict_post_hook(GraphedRegTR._bump_epoch)
         weakref.finalize(self, GraphedRegTR._release_all, self.graphs)
+
+    @staticmethod
+    def _bump_epoch(module, incompatible_keys):
+        module._weights_epoch = getattr(module, '_weights_epoch', 0) + 1
+
+    def invalidate(self):
+        """Drop every captured graph (weights were modified in place)."""
+        for key in list(self.graphs):
+            self._drop(key)
 
     @staticmethod
     def _release_all(graphs):
@@ -346,6 +361,9 @@ class GraphedRegTR:
         n0 = sum(lens0)
         cap0 = max(self.bucket, (n0 + self.bucket - 1) // self.bucket * self.bucket)
         key = (B, cap0)
+        if self._epoch != self.model._weights_epoch:          # weights were reloaded since the graphs were captured
+            self.invalidate()
+            self._epoch = self.model._weights_epoch
         st = self.graphs.get(key)
         if st is None:
             st = self.graphs[key] = self._capture(B, cap0)

@@ -242,6 +242,23 @@ def test_variant_forward_vs_reference_golden(case):
                                  logit_atol=2e-4, pose_atol=1e-4)
 
 
+def test_graph_executor_recaptures_after_load_state_dict():
+    """The captured graphs hold pointers to the split TF32 weights: reloading the weights must not leave a graph
+    replaying the old ones."""
+    from regtr_b200.regtr import GraphedRegTR, RegTR
+    from regtr_b200.weights import random_state_dict
+    cfg, sd, src, tgt = make_case('fwd_modelnet_b1')
+    model = RegTR(cfg).to(DEV).eval()
+    model.load_state_dict(sd, strict=True)
+    runner = GraphedRegTR(model, bucket=2048, ratio=1.0)
+    batch = lambda: {'src_xyz': [G(a) for a in src], 'tgt_xyz': [G(a) for a in tgt]}
+    p0 = N(runner(batch())['pose']).copy()
+    model.load_state_dict(random_state_dict(cfg, 777), strict=True)
+    p1 = N(runner(batch())['pose']).copy()
+    want = N(model(batch())['pose'])
+    assert np.abs(p1 - want).max() <= 1e-5 and np.abs(p1 - p0).max() > 1e-3
+
+
 def test_variant_forward_through_graph_executor():
     """The attention decoder + learned embedding also run capacity-shaped inside a CUDA graph."""
     from regtr_b200.regtr import GraphedRegTR, RegTR
