@@ -35,6 +35,14 @@ __device__ __forceinline__ int regtr_cloud_of(const int32_t* __restrict__ offs, 
     return lo;
 }
 
+// (row, column group) of flat work item t for a row of `w` items: 32-bit arithmetic, a shift when w is a power of two
+// (a 64-bit divide costs ~100 issue slots -- more than the rest of an elementwise kernel).  Callers bound the grid
+// so that t < 2^31.
+__device__ __forceinline__ void regtr_row_col(unsigned t, unsigned w, int& row, int& col) {
+    if ((w & (w - 1u)) == 0u) { const int sh = 31 - __clz((int)w); row = (int)(t >> sh); col = (int)(t & (w - 1u)); }
+    else { row = (int)(t / w); col = (int)(t - (unsigned)row * w); }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -658,7 +658,8 @@ __global__ void k_max_pool(const float* __restrict__ x, const int32_t* __restric
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)Nq * c4) return;
     if (ns_dev) Ns = min(Ns, *ns_dev);
-    const int qi = (int)(t / c4), cc = (int)(t % c4);
+    int qi, cc;
+    regtr_row_col((unsigned)t, (unsigned)c4, qi, cc);
     float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     for (int k = 0; k < K; ++k) {
         const int id = idx[(size_t)qi * K + k];
@@ -674,7 +675,8 @@ __global__ void k_max_pool_scalar(const float* __restrict__ x, const int32_t* __
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)Nq * C) return;
     if (ns_dev) Ns = min(Ns, *ns_dev);
-    const int qi = (int)(t / C), c = (int)(t % C);
+    int qi, c;
+    regtr_row_col((unsigned)t, (unsigned)C, qi, c);
     float m = -INFINITY;
     for (int k = 0; k < K; ++k) {
         const int id = idx[(size_t)qi * K + k];
@@ -694,7 +696,9 @@ __global__ void k_gemm_smallk(const float* __restrict__ a, const float* __restri
     const int c4 = Cout >> 2;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)n * c4) return;
-    const int r = (int)(t / c4), c = (int)(t % c4) * 4;
+    int r, c;
+    regtr_row_col((unsigned)t, (unsigned)c4, r, c);
+    c *= 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int k = 0; k < K; ++k) {
         const float av = a[(size_t)r * K + k];
@@ -916,6 +920,7 @@ int regtr_max_pool(const float* x, const int32_t* idx, int Nq, int Ns, const int
                    float* out, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (Nq < 0 || Ns < 0 || K <= 0 || C <= 0) return REGTR_ERR_ARG;
+    if ((long long)Nq * C >= (1ll << 31)) return REGTR_ERR_UNSUPPORTED;               // 32-bit work-item index
     if (Nq == 0) return REGTR_OK;
     if (!x || !idx || !out) return REGTR_ERR_ARG;
     if (C % 4 == 0) {

@@ -153,7 +153,8 @@ __global__ void k_in_apply(const float* x, const int32_t* __restrict__ offs, int
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in_range = t < (long long)n_cap * c4n;
     if (!FLAGS && !in_range) return;
-    const int r = in_range ? (int)(t / c4n) : 0, c = in_range ? (int)(t % c4n) * 4 : 0;
+    int r = 0, c = 0;
+    if (in_range) { regtr_row_col((unsigned)t, (unsigned)c4n, r, c); c *= 4; }
     const size_t o = (size_t)r * C + c;
     const int n_real = offs[n_clouds];
     const bool live = in_range && r < n_real;                  // rows beyond the real count are capacity padding
@@ -218,7 +219,8 @@ __global__ void k_pos_embed_sine(const float* __restrict__ xyz, int n, const flo
                                  int d_model, float scale, float* __restrict__ out) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)n * d_model) return;
-    const int i = (int)(t / d_model), c = (int)(t % d_model);
+    int i, c;
+    regtr_row_col((unsigned)t, (unsigned)d_model, i, c);
     float o = 0.f;
     if (c < 3 * n_freq) {
         const int a = c / n_freq, f = c % n_freq;
@@ -248,7 +250,7 @@ int regtr_instnorm_act(const float* x, const int32_t* offs, int n_clouds, int n_
                        int32_t* counters, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (!offs || n_clouds <= 0 || n_cap < 0 || C <= 0) return REGTR_ERR_ARG;
-    if (C % 4 != 0) return REGTR_ERR_UNSUPPORTED;
+    if (C % 4 != 0 || (long long)n_cap * (C / 4) >= (1ll << 31)) return REGTR_ERR_UNSUPPORTED;   // 32-bit work-item index
     if (n_cap == 0) return REGTR_OK;
     if (!x || !out || !ws) return REGTR_ERR_ARG;
     if (ws_bytes < regtr_instnorm_ws_bytes(n_cap, n_clouds, C)) return REGTR_ERR_WORKSPACE;
@@ -280,7 +282,7 @@ int regtr_instnorm_apply(const float* x, const int32_t* offs, int n_clouds, int 
                          const float* res, float slope, float* out, uint8_t* rowflag_out, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (!offs || n_clouds <= 0 || n_cap < 0 || C <= 0) return REGTR_ERR_ARG;
-    if (C % 4 != 0) return REGTR_ERR_UNSUPPORTED;
+    if (C % 4 != 0 || (long long)n_cap * (C / 4) >= (1ll << 31)) return REGTR_ERR_UNSUPPORTED;   // 32-bit work-item index
     if (n_cap == 0) return REGTR_OK;
     if (!x || !out || !stats) return REGTR_ERR_ARG;
     const float2* stp = reinterpret_cast<const float2*>(stats);
@@ -312,6 +314,7 @@ int regtr_pos_embed_sine(const float* xyz, int n, const float* dim_t, int n_freq
                          float* out, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (n < 0 || n_freq <= 0 || d_model < 3 * n_freq) return REGTR_ERR_ARG;
+    if ((long long)n * d_model >= (1ll << 31)) return REGTR_ERR_UNSUPPORTED;
     if (n == 0) return REGTR_OK;
     if (!xyz || !dim_t || !out) return REGTR_ERR_ARG;
     k_pos_embed_sine<<<regtr_cdiv((long long)n * d_model, 256), 256, 0, st>>>(xyz, n, dim_t, n_freq, d_model, scale, out);

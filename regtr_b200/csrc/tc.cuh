@@ -31,9 +31,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"     // %3: suspend-time hint (ns): the
+            "selp.u32 %0, 1, 0, p;\n\t}"                                      // warp sleeps in hardware, not in a poll loop
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
         if (done) return;
         if (spin > (1u << 28)) __trap();
     }
