@@ -175,12 +175,22 @@ k_gemm_tf32x3_ts(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tmem_full = afree + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
+    const int nkb_total = (K + BK - 1) / BK;
+    const int kb0 = blockIdx.z * kb_per_split;
+    const int nkb = min(kb_per_split, nkb_total - kb0);
+    const int n_pre = min(nkb, P::STAGES);                 // k-blocks whose loads start before the set-up barrier
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < P::STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { tc::mbar_init(&aready[b], 4); tc::mbar_init(&afree[b], 1); }
         tc::mbar_init(tmem_full, 1);
         tc::fence_barrier_init();
-        tc::tma_prefetch_desc(&tmA); tc::tma_prefetch_desc(&tmBhi); tc::tma_prefetch_desc(&tmBlo);
+        // the first loads do not need tensor memory: they fly while warp 1 allocates it
+        for (int kb = 0; kb < n_pre; ++kb) {
+            tc::mbar_arrive_expect_tx(&full[kb], P::A_BYTES + 2 * P::B_BYTES);
+            tc::tma_load_2d(stage_A(kb), &tmA, &full[kb], (kb0 + kb) * BK, m0);
+            tc::tma_load_2d(stage_Bhi(kb), &tmBhi, &full[kb], (kb0 + kb) * BK, n0);
+            tc::tma_load_2d(stage_Blo(kb), &tmBlo, &full[kb], (kb0 + kb) * BK, n0);
+        }
     }
     if (warp == 1) tc::tmem_alloc<P::TMEM_COLS>(tmem_slot);
     tc::fence_before_thread_sync();
@@ -188,14 +198,11 @@ k_gemm_tf32x3_ts(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc::fence_after_thread_sync();
     const uint32_t tmem_d = *tmem_slot;
     const uint32_t tmem_a = tmem_d + (uint32_t)P::ACC_COLS;
-    const int nkb_total = (K + BK - 1) / BK;
-    const int kb0 = blockIdx.z * kb_per_split;
-    const int nkb = min(kb_per_split, nkb_total - kb0);
     C += (size_t)blockIdx.z * split_stride;
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = n_pre; kb < nkb; ++kb) {
                 const int s = kb % P::STAGES;
                 const uint32_t ph = (kb / P::STAGES) & 1;
                 tc::mbar_wait(&empty[s], ph ^ 1);
@@ -424,9 +431,18 @@ __global__ void k_splitk_reduce(const float* __restrict__ P, int splits, size_t 
     int r, c;
     regtr_row_col((unsigned)t, (unsigned)n4, r, c);
     c *= 4;
-    float4 acc = *reinterpret_cast<const float4*>(P + (size_t)r * N + c);
-    for (int z = 1; z < splits; ++z) {
-        const float4 v = *reinterpret_cast<const float4*>(P + (size_t)z * split_stride + (size_t)r * N + c);
+    const float* p0 = P + (size_t)r * N + c;
+    float4 acc = *reinterpret_cast<const float4*>(p0);
+    int z = 1;
+    for (; z + 4 <= splits; z += 4) {                  // four planes in flight; the sum keeps the plane order
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(p0 + (size_t)(z + u) * split_stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    for (; z < splits; ++z) {
+        const float4 v = *reinterpret_cast<const float4*>(p0 + (size_t)z * split_stride);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     if (bias) { acc.x += bias[c]; acc.y += bias[c + 1]; acc.z += bias[c + 2]; acc.w += bias[c + 3]; }

@@ -156,20 +156,23 @@ __global__ void k_in_apply(const float* x, const int32_t* __restrict__ offs, int
     int r = 0, c = 0;
     if (in_range) { regtr_row_col((unsigned)t, (unsigned)c4n, r, c); c *= 4; }
     const size_t o = (size_t)r * C + c;
+    // the row's data is requested before anything that depends on the offsets table (capacity buffers: every row
+    // below n_cap is readable), so the x / residual loads overlap the offsets -> cloud -> statistics chain
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), rv = v;
+    if (in_range) {
+        v = *reinterpret_cast<const float4*>(x + o);
+        if (res) rv = *reinterpret_cast<const float4*>(res + o);
+    }
     const int n_real = offs[n_clouds];
     const bool live = in_range && r < n_real;                  // rows beyond the real count are capacity padding
     float y[4] = {0.f, 0.f, 0.f, 0.f};
     if (live) {
         const int cloud = regtr_cloud_of(offs, n_clouds, r);
-        const float4 v = *reinterpret_cast<const float4*>(x + o);
         const float4 st01 = *reinterpret_cast<const float4*>(stats + (size_t)cloud * C + c);
         const float4 st23 = *reinterpret_cast<const float4*>(stats + (size_t)cloud * C + c + 2);
         y[0] = (v.x - st01.x) * st01.y; y[1] = (v.y - st01.z) * st01.w;
         y[2] = (v.z - st23.x) * st23.y; y[3] = (v.w - st23.z) * st23.w;
-        if (res) {
-            const float4 rv = *reinterpret_cast<const float4*>(res + o);
-            y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w;
-        }
+        if (res) { y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w; }
         if (slope >= 0.f) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) y[j] = y[j] > 0.f ? y[j] : y[j] * slope;
@@ -185,7 +188,8 @@ __global__ void k_in_apply(const float* x, const int32_t* __restrict__ offs, int
     }
 }
 
-// One warp per row; E <= 1024, multiple of 32.
+// One warp per row; E = 32 * per <= 32 * PER (PER = 8: the model width 256; PER = 32: anything up to 1024).
+template <int PER>
 __global__ void k_layernorm_pos(const float* __restrict__ x, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const float* __restrict__ pos, int n,
                                 const int32_t* __restrict__ n_dev, int E, float eps, float* __restrict__ y,
@@ -194,23 +198,31 @@ __global__ void k_layernorm_pos(const float* __restrict__ x, const float* __rest
     if (n_dev) n = min(n, *n_dev);               // capacity-shaped launch: rows beyond the real count are skipped
     if (row >= n) return;
     const float* xr = x + (size_t)row * E;
-    float v[32];
     const int per = E / 32;
+    // every operand is requested before the first reduction: one memory round trip instead of three dependent ones
+    float v[PER], gm[PER], bt[PER], ps[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+        if (j < per) {
+            const int c = j * 32 + lane;
+            v[j] = xr[c]; gm[j] = __ldg(gamma + c); bt[j] = __ldg(beta + c);
+            ps[j] = (y_pos && pos) ? pos[(size_t)row * E + c] : 0.f;
+        }
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) if (j < per) { v[j] = xr[j * 32 + lane]; s += v[j]; }
+    for (int j = 0; j < PER; ++j) if (j < per) s += v[j];
     const float mean = warp_sum(s) / (float)E;
     float ss = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) if (j < per) { const float d = v[j] - mean; ss += d * d; }
+    for (int j = 0; j < PER; ++j) if (j < per) { const float d = v[j] - mean; ss += d * d; }
     const float rstd = 1.f / sqrtf(warp_sum(ss) / (float)E + eps);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < PER; ++j) {
         if (j >= per) break;
         const int c = j * 32 + lane;
-        const float o = (v[j] - mean) * rstd * gamma[c] + beta[c];
+        const float o = (v[j] - mean) * rstd * gm[j] + bt[j];
         if (y) y[(size_t)row * E + c] = o;
-        if (y_pos) y_pos[(size_t)row * E + c] = o + (pos ? pos[(size_t)row * E + c] : 0.f);
+        if (y_pos) y_pos[(size_t)row * E + c] = o + ps[j];
     }
 }
 
@@ -305,7 +317,10 @@ int regtr_layernorm_pos(const float* x, const float* gamma, const float* beta, c
     if (n < 0 || E <= 0 || E % 32 != 0 || E > 1024) return REGTR_ERR_ARG;
     if (n == 0) return REGTR_OK;
     if (!x || !gamma || !beta || (!y && !y_pos)) return REGTR_ERR_ARG;
-    k_layernorm_pos<<<regtr_cdiv((long long)n * 32, 256), 256, 0, st>>>(x, gamma, beta, pos, n, n_dev, E, eps, y, y_pos);
+    if (E <= 256)
+        k_layernorm_pos<8><<<regtr_cdiv((long long)n * 32, 256), 256, 0, st>>>(x, gamma, beta, pos, n, n_dev, E, eps, y, y_pos);
+    else
+        k_layernorm_pos<32><<<regtr_cdiv((long long)n * 32, 256), 256, 0, st>>>(x, gamma, beta, pos, n, n_dev, E, eps, y, y_pos);
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
 }
