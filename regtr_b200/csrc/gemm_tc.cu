@@ -420,6 +420,214 @@ k_gemm_tf32x3_ts(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1) tc::tmem_dealloc<P::TMEM_COLS>(tmem_d);
 }
 
+// ---- persistent variant for launches of several waves (M >= ~40 000 rows) ------------------------------------------
+// One-tile CTAs pay the set-up (barriers, tensor-memory allocation, descriptor fetch) and a full TMA round trip per
+// tile; with K = 32..128 that is most of the ~11 us a tile takes (ncu: converter warps wait on TMA 24 % of samples).
+// Here a CTA walks tiles blockIdx.x, + gridDim.x, ...: the barriers' stage / phase counters run across tiles, the TMA
+// warp loads the next tile while the converter warps run the epilogue of the current one, the MMA warp waits for the
+// accumulator to be drained (tmem_empty) before it starts the next tile.  Plain epilogue (bias / residual / ReLU) and
+// the InstanceNorm partials only; no split-K.  The epilogue stages 16 rows at a time through its own 9 KB of shared
+// memory (the pipeline stages are busy with the next tile).
+template <int BN, int NACC, int ST> struct CfgP : CfgT<BN, NACC, ST> {
+    static constexpr int EPI_BYTES = 4 * 16 * 36 * 4;
+    static constexpr int SMEM = CfgT<BN, NACC, ST>::SMEM + EPI_BYTES;
+};
+
+template <int BN, int NACC, int ST>
+__global__ void __launch_bounds__(192, 2)
+k_gemm_tf32x3_persist(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                      const __grid_constant__ CUtensorMap tmBlo, float* __restrict__ C, int ldc,
+                      const float* __restrict__ bias, const float* __restrict__ R, int ldr, int M, int N, int K,
+                      const int32_t* __restrict__ m_dev, int relu, float2* __restrict__ part) {
+    using P = CfgP<BN, NACC, ST>;
+    static_assert(P::TMEM_COLS <= 256 && P::SMEM <= 113 * 1024, "two CTAs per SM");
+    extern __shared__ unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (m_dev) M = min(M, *m_dev);
+    const int tiles_n = (N + BN - 1) / BN;
+    const int n_tiles = ((M + BM - 1) / BM) * tiles_n;       // tiles that hold real rows
+    if ((int)blockIdx.x >= n_tiles) return;                  // uniform exit
+
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    auto stage_A = [&](int s) { return base + s * P::STAGE_BYTES; };
+    auto stage_Bhi = [&](int s) { return base + s * P::STAGE_BYTES + P::A_BYTES; };
+    auto stage_Blo = [&](int s) { return base + s * P::STAGE_BYTES + P::A_BYTES + P::B_BYTES; };
+    float* epi = reinterpret_cast<float*>(base + P::STAGES * P::STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + P::STAGES * P::STAGE_BYTES + P::EPI_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + P::STAGES;
+    uint64_t* aready = bars + 2 * P::STAGES;
+    uint64_t* afree = aready + 2;
+    uint64_t* tmem_full = afree + 2;
+    uint64_t* tmem_empty = tmem_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < P::STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(&aready[b], 4); tc::mbar_init(&afree[b], 1); }
+        tc::mbar_init(tmem_full, 1);
+        tc::mbar_init(tmem_empty, 4);
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&tmA); tc::tma_prefetch_desc(&tmBhi); tc::tma_prefetch_desc(&tmBlo);
+    }
+    if (warp == 1) tc::tmem_alloc<P::TMEM_COLS>(tmem_slot);
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    tc::fence_after_thread_sync();
+    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t tmem_a = tmem_d + (uint32_t)P::ACC_COLS;
+    const int nkb = (K + BK - 1) / BK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;                                         // k-block counter across tiles
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % P::STAGES;
+                    const uint32_t ph = (it / P::STAGES) & 1;
+                    tc::mbar_wait(&empty[s], ph ^ 1);
+                    tc::mbar_arrive_expect_tx(&full[s], P::A_BYTES + 2 * P::B_BYTES);
+                    tc::tma_load_2d(stage_A(s), &tmA, &full[s], kb * BK, m0);
+                    tc::tma_load_2d(stage_Bhi(s), &tmBhi, &full[s], kb * BK, n0);
+                    tc::tma_load_2d(stage_Blo(s), &tmBlo, &full[s], kb * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::umma_idesc(tc::FMT_TF32, BM, BN);
+            int it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+                if (tcount > 0) {                               // the epilogue of the previous tile has drained the accumulator
+                    tc::mbar_wait(tmem_empty, (tcount - 1) & 1);
+                    tc::fence_after_thread_sync();
+                }
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % P::STAGES, ab = it & 1;
+                    const uint32_t ph = (it / P::STAGES) & 1, aph = (it >> 1) & 1;
+                    tc::mbar_wait(&full[s], ph);
+                    tc::mbar_wait(&aready[ab], aph);
+                    tc::fence_after_thread_sync();
+                    const uint64_t dBhi = tc::umma_desc_sw128_kmajor(tc::smem_u32(stage_Bhi(s)));
+                    const uint64_t dBlo = tc::umma_desc_sw128_kmajor(tc::smem_u32(stage_Blo(s)));
+                    const uint32_t a_hi = tmem_a + (uint32_t)(ab * 2 * BK), a_lo = a_hi + BK;
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);
+                        const uint32_t acc = tmem_d + (uint32_t)((k % NACC) * BN);
+                        const uint32_t first = (kb == 0 && k < NACC) ? 0u : 1u;
+                        tc::umma_tf32_ts(acc, a_lo + 8 * k, dBhi + adv, idesc, first);
+                        tc::umma_tf32_ts(acc, a_hi + 8 * k, dBlo + adv, idesc, 1);
+                        tc::umma_tf32_ts(acc, a_hi + 8 * k, dBhi + adv, idesc, 1);
+                    }
+                    tc::umma_commit(&empty[s]);
+                    tc::umma_commit(&afree[ab]);
+                }
+                tc::umma_commit(tmem_full);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        float* tile_s = epi + q * (16 * 36);
+        int it = 0, tcount = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+            const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % P::STAGES, ab = it & 1;
+                const uint32_t ph = (it / P::STAGES) & 1, aph = (it >> 1) & 1;
+                tc::mbar_wait(&full[s], ph);
+                tc::mbar_wait(&afree[ab], aph ^ 1);
+                tc::fence_after_thread_sync();
+                const unsigned char* rowp = stage_A(s) + r * 128;
+                const uint32_t dst = tmem_a + lane_sel + (uint32_t)(ab * 2 * BK);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 v = *reinterpret_cast<const float4*>(rowp + (((half * 4 + c) ^ (r & 7)) << 4));
+                        const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t h = (__float_as_uint(f[e]) + 0x1000u) & HI_MASK;
+                            hi[4 * c + e] = h;
+                            lo[4 * c + e] = (__float_as_uint(f[e] - __uint_as_float(h)) + 0x1000u) & HI_MASK;
+                        }
+                    }
+                    tc::tmem_st_32x16(dst + 16 * half, hi);
+                    tc::tmem_st_32x16(dst + BK + 16 * half, lo);
+                }
+                tc::tmem_st_wait();
+                tc::fence_before_thread_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&aready[ab]);
+            }
+            // ---- epilogue of this tile
+            tc::mbar_wait(tmem_full, tcount & 1);
+            tc::fence_after_thread_sync();
+            const int row_base = m0 + q * 32;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tc::tmem_ld_32x32(tmem_d + lane_sel + (uint32_t)c0, v);
+#pragma unroll
+                for (int a = 1; a < NACC; ++a) {
+                    float u[32];
+                    tc::tmem_ld_32x32(tmem_d + lane_sel + (uint32_t)(a * BN + c0), u);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += u[j];
+                }
+                const int col0 = n0 + c0;
+                if (col0 >= N) continue;                           // warp-uniform (N % 32 == 0 on this path)
+                const int cq = lane & 7, rsub = lane >> 3;
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias) b4 = *reinterpret_cast<const float4*>(bias + col0 + 4 * cq);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {             // 16 rows at a time through shared memory
+                    if ((lane >> 4) == half) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(tile_s + (lane & 15) * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i4 = 0; i4 < 4; ++i4) {
+                        const int rr = i4 * 4 + rsub, rg = row_base + 16 * half + rr;
+                        float4 o = *reinterpret_cast<const float4*>(tile_s + rr * 36 + 4 * cq);
+                        if (rg < M) {
+                            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+                            if (R) {
+                                const float4 rv = *reinterpret_cast<const float4*>(R + (size_t)rg * ldr + col0 + 4 * cq);
+                                o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+                            }
+                            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            *reinterpret_cast<float4*>(C + (size_t)rg * ldc + col0 + 4 * cq) = o;
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (part) {
+                    float sq[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+                    const float s1 = warp_transpose_sum(v, lane);
+                    const float s2 = warp_transpose_sum(sq, lane);
+                    part[(size_t)((m0 >> 5) + q) * N + col0 + lane] = make_float2(s1, s2);
+                }
+            }
+            tc::fence_before_thread_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tmem_empty);            // the accumulator may be overwritten
+        }
+    }
+    tc::fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<P::TMEM_COLS>(tmem_d);
+}
+
 // C = act(sum_z P[z] + bias + R): deterministic split-K reduction (fixed order), 4 columns / thread
 __global__ void k_splitk_reduce(const float* __restrict__ P, int splits, size_t split_stride, float* __restrict__ C,
                                 int ldc, const float* __restrict__ bias, const float* __restrict__ R, int ldr, int M,
@@ -565,6 +773,27 @@ int launch_gemm_ts(const float* A, int lda, const float* Bhi, const float* Blo, 
     return REGTR_OK;
 }
 
+template <int BN, int NACC, int ST>
+int launch_gemm_persist(const float* A, int lda, const float* Bhi, const float* Blo, int ldb, float* C, int ldc,
+                        const float* bias, const float* R, int ldr, int M, int N, int K, const int32_t* m_dev, int relu,
+                        cudaStream_t st, float2* part) {
+    using P = CfgP<BN, NACC, ST>;
+    CUtensorMap tA, tBh, tBl;
+    if (!make_map(&tA, A, M, K, lda, BM) || !make_map(&tBh, Bhi, N, K, ldb, BN) || !make_map(&tBl, Blo, N, K, ldb, BN))
+        return REGTR_ERR_ARG;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tf32x3_persist<BN, NACC, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM);
+        if (e != cudaSuccess) return -(1000 + (int)e);
+        attr_set = true;
+    }
+    const int tiles = regtr_cdiv(M, BM) * regtr_cdiv(N, BN);
+    const int grid = tiles < 2 * REGTR_NUM_SMS ? tiles : 2 * REGTR_NUM_SMS;
+    k_gemm_tf32x3_persist<BN, NACC, ST><<<grid, 192, P::SMEM, st>>>(tA, tBh, tBl, C, ldc, bias, R, ldr, M, N, K, m_dev, relu, part);
+    REGTR_CHECK_LAUNCH();
+    return REGTR_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -613,6 +842,17 @@ static int gemm_dispatch(const float* A, int lda, const float* B_hi, const float
     if (splits > 1 && (!ws || ws_bytes < regtr_gemm_ws_bytes(M, N, K))) return REGTR_ERR_WORKSPACE;
     // accumulation runs per TMEM accumulator: k-blocks per split / NACC (the tensor core adds with truncation)
     const int nkb_split = regtr_cdiv(regtr_cdiv(K, BK), splits);
+    // several waves of short tiles: the persistent kernel (one set-up per CTA, loads of the next tile under the epilogue)
+    {
+        static const int persist_on = [] { const char* e = getenv("REGTR_GEMM_PERSIST"); return e ? atoi(e) : 1; }();
+        const int tiles = regtr_cdiv(M, BM) * regtr_cdiv(N, bn);
+        if (persist_on && splits == 1 && tiles > 2 * REGTR_NUM_SMS && (bn != 128 || nkb_split <= 16) && (N & 31) == 0 && (ldc & 3) == 0 &&
+            (!R || (ldr & 3) == 0)) {
+            if (bn == 128) return launch_gemm_persist<128, 1, 2>(A, lda, B_hi, B_lo, ldb, C, ldc, bias, R, ldr, M, N, K, m_dev, relu, st, part);
+            if (bn == 64) return launch_gemm_persist<64, 2, 3>(A, lda, B_hi, B_lo, ldb, C, ldc, bias, R, ldr, M, N, K, m_dev, relu, st, part);
+            return launch_gemm_persist<32, 4, 4>(A, lda, B_hi, B_lo, ldb, C, ldc, bias, R, ldr, M, N, K, m_dev, relu, st, part);
+        }
+    }
 #define REGTR_TS_CASE(BN_, NACC_, ST_)                                                                                 \
     return launch_gemm_ts<BN_, NACC_, ST_>(A, lda, B_hi, B_lo, ldb, C, ldc, bias, R, ldr, M, N, K, m_dev, relu, splits, \
                                            (float*)ws, st, NO_QKV, splits > 1 ? nullptr : part)

@@ -740,6 +740,41 @@ def N_(t):
     return t.detach().cpu().numpy()
 
 
+@pytest.mark.parametrize('N,K', [(32, 64), (32, 480), (64, 960), (128, 32), (128, 64), (256, 64)])
+def test_gemm_persistent_tiles_vs_float64(N, K):
+    """Launches of several waves take the persistent kernel (tile loop per CTA, barrier phases running across tiles,
+    accumulator hand-over between MMA and epilogue): bias / residual / ReLU, a device-side row count that ends inside
+    a tile, InstanceNorm partials of two clouds, all against float64; repeated calls bit-identical."""
+    from regtr_b200 import ops
+    rng = np.random.default_rng(N * 1000 + K)
+    cap, M = 46000, 44321                                      # 360 row tiles > 2 x 148; the last real tile is partial
+    a = np.zeros((cap, K), dtype=np.float32)
+    a[:M] = rng.normal(size=(M, K)) * 0.9 + 0.2
+    a[M:] = 7e2
+    w = (rng.normal(size=(N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.normal(size=N).astype(np.float32)
+    res = rng.normal(size=(cap, N)).astype(np.float32)
+    lens = [20000, M - 20000]
+    offs = ops.make_offsets(lens, DEV)
+    m_dev = offs[2:3]
+    hi, lo = ops.split_weight(G(w))
+    A, Rr, Bb = G(a), G(res), G(b)
+    c64 = a[:M].astype(np.float64) @ w.astype(np.float64).T
+    tol = 1e-5 * np.abs(c64).max() * max(1.0, (K / 256) ** 0.5)
+    out = ops.gemm(A, hi, lo, bias=Bb, residual=Rr, relu=True, m_dev=m_dev)
+    want = np.maximum(c64 + b.astype(np.float64) + res[:M].astype(np.float64), 0.0)
+    assert np.abs(N_(out)[:M] - want).max() <= tol + 1e-6
+    out2 = ops.gemm(A, hi, lo, bias=Bb, residual=Rr, relu=True, m_dev=m_dev)
+    assert torch.equal(out[:M], out2[:M])
+    c, stats = ops.gemm_instats(A, hi, lo, offs, 2, m_dev=m_dev)
+    assert np.abs(N_(c)[:M] - c64).max() <= tol
+    st = N_(stats)
+    for ci, (s0, s1) in enumerate(((0, lens[0]), (lens[0], M))):
+        blk = c64[s0:s1]
+        np.testing.assert_allclose(st[ci, :, 0], blk.mean(0), rtol=0, atol=2e-6 * max(1.0, np.abs(c64).max()))
+        np.testing.assert_allclose(st[ci, :, 1], 1.0 / np.sqrt(blk.var(0) + 1e-5), rtol=2e-5, atol=0)
+
+
 # ------------------------------------------------- N1 + N2 through the GPU once (SURVEY.md 8f)
 
 def test_benchmark_loop_on_real_sample_pairs_through_graph_executor(tmp_path):
