@@ -420,7 +420,7 @@ k_gemm_tf32x3_ts(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1) tc::tmem_dealloc<P::TMEM_COLS>(tmem_d);
 }
 
-// ---- persistent variant for launches of several waves (M >= ~40 000 rows) ------------------------------------------
+// ---- persistent variant (every launch of more than 37 tiles) ------------------------------------------------------
 // One-tile CTAs pay the set-up (barriers, tensor-memory allocation, descriptor fetch) and a full TMA round trip per
 // tile; with K = 32..128 that is most of the ~11 us a tile takes (ncu: converter warps wait on TMA 24 % of samples).
 // Here a CTA walks tiles blockIdx.x, + gridDim.x, ...: the barriers' stage / phase counters run across tiles, the TMA
@@ -788,7 +788,11 @@ int launch_gemm_persist(const float* A, int lda, const float* Bhi, const float* 
         attr_set = true;
     }
     const int tiles = regtr_cdiv(M, BM) * regtr_cdiv(N, BN);
-    const int grid = tiles < 2 * REGTR_NUM_SMS ? tiles : 2 * REGTR_NUM_SMS;
+    // At least ~4 tiles per CTA, between 74 CTAs (half the SMs: small launches amortise their set-up and leave room for
+    // the other forwards' kernels -- swept 6..296: 1 pair/step 1226 -> 1281 pairs/s, 8 pairs/step 1617 -> 1650) and 296.
+    int grid = tiles / 4;
+    grid = grid < REGTR_NUM_SMS / 2 ? REGTR_NUM_SMS / 2 : (grid > 2 * REGTR_NUM_SMS ? 2 * REGTR_NUM_SMS : grid);
+    if (grid > tiles) grid = tiles;
     k_gemm_tf32x3_persist<BN, NACC, ST><<<grid, 192, P::SMEM, st>>>(tA, tBh, tBl, C, ldc, bias, R, ldr, M, N, K, m_dev, relu, part);
     REGTR_CHECK_LAUNCH();
     return REGTR_OK;
@@ -846,7 +850,7 @@ static int gemm_dispatch(const float* A, int lda, const float* B_hi, const float
     {
         static const int persist_on = [] { const char* e = getenv("REGTR_GEMM_PERSIST"); return e ? atoi(e) : 1; }();
         const int tiles = regtr_cdiv(M, BM) * regtr_cdiv(N, bn);
-        if (persist_on && splits == 1 && tiles > 2 * REGTR_NUM_SMS && (bn != 128 || nkb_split <= 16) && (N & 31) == 0 && (ldc & 3) == 0 &&
+        if (persist_on && splits == 1 && tiles > REGTR_NUM_SMS / 4 && (bn != 128 || nkb_split <= 16) && (N & 31) == 0 && (ldc & 3) == 0 &&
             (!R || (ldr & 3) == 0)) {
             if (bn == 128) return launch_gemm_persist<128, 1, 2>(A, lda, B_hi, B_lo, ldb, C, ldc, bias, R, ldr, M, N, K, m_dev, relu, st, part);
             if (bn == 64) return launch_gemm_persist<64, 2, 3>(A, lda, B_hi, B_lo, ldb, C, ldc, bias, R, ldr, M, N, K, m_dev, relu, st, part);

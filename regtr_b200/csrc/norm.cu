@@ -150,41 +150,41 @@ __global__ void k_in_apply(const float* x, const int32_t* __restrict__ offs, int
                            const float2* __restrict__ stats, const float* res, float slope, float* out,
                            uint8_t* __restrict__ flags) {
     const int c4n = C >> 2;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in_range = t < (long long)n_cap * c4n;
-    if (!FLAGS && !in_range) return;
-    int r = 0, c = 0;
-    if (in_range) { regtr_row_col((unsigned)t, (unsigned)c4n, r, c); c *= 4; }
-    const size_t o = (size_t)r * C + c;
-    // the row's data is requested before anything that depends on the offsets table (capacity buffers: every row
-    // below n_cap is readable), so the x / residual loads overlap the offsets -> cloud -> statistics chain
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), rv = v;
-    if (in_range) {
-        v = *reinterpret_cast<const float4*>(x + o);
-        if (res) rv = *reinterpret_cast<const float4*>(res + o);
-    }
+    // grid-stride over float4 items (a few thousand long-lived CTAs instead of one item per thread: the offsets
+    // chain is paid once per thread and the CTA launch cost once per ~10 items).  Only rows below the 128-row tile
+    // that straddles the real count are touched: zeros in its padding part (the only padding a consumer -- a
+    // tiled GEMM -- can read), nothing beyond.
     const int n_real = offs[n_clouds];
-    const bool live = in_range && r < n_real;                  // rows beyond the real count are capacity padding
-    float y[4] = {0.f, 0.f, 0.f, 0.f};
-    if (live) {
-        const int cloud = regtr_cloud_of(offs, n_clouds, r);
-        const float4 st01 = *reinterpret_cast<const float4*>(stats + (size_t)cloud * C + c);
-        const float4 st23 = *reinterpret_cast<const float4*>(stats + (size_t)cloud * C + c + 2);
-        y[0] = (v.x - st01.x) * st01.y; y[1] = (v.y - st01.z) * st01.w;
-        y[2] = (v.z - st23.x) * st23.y; y[3] = (v.w - st23.z) * st23.w;
-        if (res) { y[0] += rv.x; y[1] += rv.y; y[2] += rv.z; y[3] += rv.w; }
-        if (slope >= 0.f) {
+    const unsigned total = (unsigned)min(n_cap, (n_real + 127) & ~127) * (unsigned)c4n;
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned t0 = blockIdx.x * blockDim.x; t0 < total; t0 += stride) {        // block-uniform trip count
+        const unsigned t = t0 + threadIdx.x;
+        const bool in_range = t < total;
+        int r = 0, c = 0;
+        if (in_range) { regtr_row_col(t, (unsigned)c4n, r, c); c *= 4; }
+        const size_t o = (size_t)r * C + c;
+        const bool live = in_range && r < n_real;
+        float y[4] = {0.f, 0.f, 0.f, 0.f};
+        if (live) {
+            const float4 v = *reinterpret_cast<const float4*>(x + o);
+            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (res) rv = *reinterpret_cast<const float4*>(res + o);
+            const int cloud = regtr_cloud_of(offs, n_clouds, r);
+            const float4 st01 = *reinterpret_cast<const float4*>(stats + (size_t)cloud * C + c);
+            const float4 st23 = *reinterpret_cast<const float4*>(stats + (size_t)cloud * C + c + 2);
+            y[0] = (v.x - st01.x) * st01.y + rv.x; y[1] = (v.y - st01.z) * st01.w + rv.y;
+            y[2] = (v.z - st23.x) * st23.y + rv.z; y[3] = (v.w - st23.z) * st23.w + rv.w;
+            if (slope >= 0.f) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) y[j] = y[j] > 0.f ? y[j] : y[j] * slope;
+                for (int j = 0; j < 4; ++j) y[j] = y[j] > 0.f ? y[j] : y[j] * slope;
+            }
         }
-    }
-    // padding rows: zeros inside the 128-row tile that straddles the real count (the only padding a consumer
-    // -- a tiled GEMM -- can touch), untouched beyond
-    if (in_range && r < ((n_real + 127) & ~127)) *reinterpret_cast<float4*>(out + o) = make_float4(y[0], y[1], y[2], y[3]);
-    if (FLAGS) {                                               // single convergent shuffle site for the whole warp
-        double acc = ((double)y[0] + (double)y[1]) + ((double)y[2] + (double)y[3]);
-        for (int d = 1; d < c4n; d <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-        if (in_range && (threadIdx.x & (c4n - 1)) == 0) flags[r] = live && acc > 0.0;
+        if (in_range) *reinterpret_cast<float4*>(out + o) = make_float4(y[0], y[1], y[2], y[3]);
+        if (FLAGS) {                                           // single convergent shuffle site for the whole warp
+            double acc = ((double)y[0] + (double)y[1]) + ((double)y[2] + (double)y[3]);
+            for (int d = 1; d < c4n; d <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+            if (in_range && (threadIdx.x & (c4n - 1)) == 0) flags[r] = live && acc > 0.0;
+        }
     }
 }
 
@@ -242,6 +242,11 @@ __global__ void k_pos_embed_sine(const float* __restrict__ xyz, int n, const flo
     out[t] = o;
 }
 
+static inline int in_apply_grid(long long items) {
+    const long long b = (items + 255) / 256;
+    return (int)(b < 8 * REGTR_NUM_SMS ? (b > 0 ? b : 1) : 8 * REGTR_NUM_SMS);
+}
+
 }  // namespace
 
 extern "C" {
@@ -279,10 +284,10 @@ int regtr_instnorm_act(const float* x, const int32_t* offs, int n_clouds, int n_
     if (rowflag_out) {
         const int c4n = C / 4;
         if (c4n > 32 || (c4n & (c4n - 1))) return REGTR_ERR_UNSUPPORTED;   // the row must sit inside one warp
-        k_in_apply<true><<<regtr_cdiv((long long)n_cap * c4n, 256), 256, 0, st>>>(x, offs, n_clouds, n_cap, C, stats,
+        k_in_apply<true><<<in_apply_grid((long long)n_cap * c4n), 256, 0, st>>>(x, offs, n_clouds, n_cap, C, stats,
                                                                                   res, slope, out, rowflag_out);
     } else {
-        k_in_apply<false><<<regtr_cdiv((long long)n_cap * (C / 4), 256), 256, 0, st>>>(x, offs, n_clouds, n_cap, C,
+        k_in_apply<false><<<in_apply_grid((long long)n_cap * (C / 4)), 256, 0, st>>>(x, offs, n_clouds, n_cap, C,
                                                                                       stats, res, slope, out, nullptr);
     }
     REGTR_CHECK_LAUNCH();
@@ -301,10 +306,10 @@ int regtr_instnorm_apply(const float* x, const int32_t* offs, int n_clouds, int 
     if (rowflag_out) {
         const int c4n = C / 4;
         if (c4n > 32 || (c4n & (c4n - 1))) return REGTR_ERR_UNSUPPORTED;   // the row must sit inside one warp
-        k_in_apply<true><<<regtr_cdiv((long long)n_cap * c4n, 256), 256, 0, st>>>(x, offs, n_clouds, n_cap, C, stp, res, slope,
+        k_in_apply<true><<<in_apply_grid((long long)n_cap * c4n), 256, 0, st>>>(x, offs, n_clouds, n_cap, C, stp, res, slope,
                                                                                   out, rowflag_out);
     } else {
-        k_in_apply<false><<<regtr_cdiv((long long)n_cap * (C / 4), 256), 256, 0, st>>>(x, offs, n_clouds, n_cap, C, stp, res,
+        k_in_apply<false><<<in_apply_grid((long long)n_cap * (C / 4)), 256, 0, st>>>(x, offs, n_clouds, n_cap, C, stp, res,
                                                                                       slope, out, nullptr);
     }
     REGTR_CHECK_LAUNCH();
