@@ -553,15 +553,20 @@ k_kpconv_c1(const float* __restrict__ q, const float* __restrict__ s, const int3
         for (int t = threadIdx.x; t < KP * Cout; t += blockDim.x) W_s[t] = W[t];
         __syncthreads();
     }
-    const int qi = blockIdx.x * AGG_WARPS + warp;
-    if (qi >= Nq) return;
     if (ns_dev) Ns = min(Ns, *ns_dev);
     const int width = FUSE ? Cout : KP;
+    const int nq_real = nq_dev ? min(Nq, *nq_dev) : Nq;
+    const int p = lane & 15;
+    const bool real = p < KP;                    // slot 15: a far-away kernel point, influence exactly 0
+    const float kx = real ? __ldg(kp + 3 * p) : -1e6f, ky = real ? __ldg(kp + 3 * p + 1) : -1e6f,
+                kz = real ? __ldg(kp + 3 * p + 2) : -1e6f;
+    // persistent warps: the weights are staged once per CTA, the kernel points once per warp
+    for (int qi = blockIdx.x * AGG_WARPS + warp; qi < Nq; qi += gridDim.x * AGG_WARPS) {
     float* o = out + (size_t)qi * width;
-    if (nq_dev && qi >= *nq_dev) {               // capacity padding row
-        if (qi < pad_band_end(*nq_dev))
+    if (qi >= nq_real) {                         // capacity padding row
+        if (qi < pad_band_end(nq_real))
             for (int t = lane; t < width; t += 32) o[t] = 0.f;
-        return;
+        continue;
     }
     const float qx = q[3 * qi], qy = q[3 * qi + 1], qz = q[3 * qi + 2];
     const int32_t* idx_row = idx + (size_t)qi * K;
@@ -584,10 +589,6 @@ k_kpconv_c1(const float* __restrict__ q, const float* __restrict__ s, const int3
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) counted += __shfl_xor_sync(0xffffffffu, counted, off);
     __syncwarp();
-    const int p = lane & 15;
-    const bool real = p < KP;                    // slot 15: a far-away kernel point, influence exactly 0
-    const float kx = real ? __ldg(kp + 3 * p) : -1e6f, ky = real ? __ldg(kp + 3 * p + 1) : -1e6f,
-                kz = real ? __ldg(kp + 3 * p + 2) : -1e6f;
     float acc = 0.f;
     for (int k = lane >> 4; k < base; k += 2) {
         const float4 r = rel_s[k];
@@ -610,6 +611,8 @@ k_kpconv_c1(const float* __restrict__ q, const float* __restrict__ s, const int3
             }
             if (c < Cout) o[c] = r;
         }
+    }
+    __syncwarp();                                // rel_s is refilled for the next query of this warp
     }
 }
 
@@ -655,19 +658,20 @@ k_kpconv_agg_small(const float* __restrict__ q, const float* __restrict__ s, con
 __global__ void k_max_pool(const float* __restrict__ x, const int32_t* __restrict__ idx, int Nq, int Ns,
                            const int32_t* __restrict__ ns_dev, int K, int C, float* __restrict__ out) {
     const int c4 = C >> 2;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)Nq * c4) return;
     if (ns_dev) Ns = min(Ns, *ns_dev);
-    int qi, cc;
-    regtr_row_col((unsigned)t, (unsigned)c4, qi, cc);
-    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    for (int k = 0; k < K; ++k) {
-        const int id = idx[(size_t)qi * K + k];
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (id >= 0 && id < Ns) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)id * C) + cc);
-        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    const unsigned total = (unsigned)Nq * (unsigned)c4, stride = gridDim.x * blockDim.x;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {     // grid-stride: long-lived CTAs
+        int qi, cc;
+        regtr_row_col(t, (unsigned)c4, qi, cc);
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int k = 0; k < K; ++k) {
+            const int id = idx[(size_t)qi * K + k];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (id >= 0 && id < Ns) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)id * C) + cc);
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+        reinterpret_cast<float4*>(out + (size_t)qi * C)[cc] = m;
     }
-    reinterpret_cast<float4*>(out + (size_t)qi * C)[cc] = m;
 }
 
 __global__ void k_max_pool_scalar(const float* __restrict__ x, const int32_t* __restrict__ idx, int Nq, int Ns,
@@ -779,6 +783,11 @@ bool agg_use_mma() {
 
 }  // namespace
 
+static inline int c1_grid(int Nq) {
+    const int b = regtr_cdiv(Nq, AGG_WARPS);
+    return b < 8 * REGTR_NUM_SMS ? b : 8 * REGTR_NUM_SMS;
+}
+
 extern "C" {
 
 // wf | row flags  (what regtr_kpconv_aggregate needs; regtr_kpconv_fwd adds regtr_kpconv_fwd_ws_bytes)
@@ -803,7 +812,7 @@ int regtr_kpconv_aggregate(const float* q, const float* s, const int32_t* idx, c
     if (Nq == 0) return REGTR_OK;
     if (!q || !s || !idx || !x || !kp || !wf || !rowflag_ws) return REGTR_ERR_ARG;
     if (Cin == 1 && (size_t)AGG_WARPS * K * sizeof(float4) <= 48 * 1024) {      // flags come from x itself
-        k_kpconv_c1<false><<<regtr_cdiv(Nq, AGG_WARPS), AGG_WARPS * 32, (size_t)AGG_WARPS * K * sizeof(float4), st>>>(
+        k_kpconv_c1<false><<<c1_grid(Nq), AGG_WARPS * 32, (size_t)AGG_WARPS * K * sizeof(float4), st>>>(
             q, s, idx, x, kp, nullptr, Nq, Ns, nq_dev, ns_dev, K, 0, 1.f / extent, wf);
         REGTR_CHECK_LAUNCH();
         return REGTR_OK;
@@ -882,7 +891,7 @@ int regtr_kpconv_fwd(const float* q, const float* s, const int32_t* idx, const f
         if (!q || !s || !idx || !x || !kp) return REGTR_ERR_ARG;
         const size_t smem = (size_t)AGG_WARPS * K * sizeof(float4) + (size_t)KP * Cout * sizeof(float);
         if (smem <= 48 * 1024) {
-            k_kpconv_c1<true><<<regtr_cdiv(Nq, AGG_WARPS), AGG_WARPS * 32, smem, st>>>(
+            k_kpconv_c1<true><<<c1_grid(Nq), AGG_WARPS * 32, smem, st>>>(
                 q, s, idx, x, kp, W, Nq, Ns, nq_dev, ns_dev, K, Cout, 1.f / extent, out);
             REGTR_CHECK_LAUNCH();
             return REGTR_OK;
@@ -924,7 +933,8 @@ int regtr_max_pool(const float* x, const int32_t* idx, int Nq, int Ns, const int
     if (Nq == 0) return REGTR_OK;
     if (!x || !idx || !out) return REGTR_ERR_ARG;
     if (C % 4 == 0) {
-        k_max_pool<<<regtr_cdiv((long long)Nq * (C / 4), 256), 256, 0, st>>>(x, idx, Nq, Ns, ns_dev, K, C, out);
+        const int mp_blocks = regtr_cdiv((long long)Nq * (C / 4), 256);
+        k_max_pool<<<mp_blocks < 8 * REGTR_NUM_SMS ? mp_blocks : 8 * REGTR_NUM_SMS, 256, 0, st>>>(x, idx, Nq, Ns, ns_dev, K, C, out);
     } else {
         k_max_pool_scalar<<<regtr_cdiv((long long)Nq * C, 256), 256, 0, st>>>(x, idx, Nq, Ns, ns_dev, K, C, out);
     }

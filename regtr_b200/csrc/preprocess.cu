@@ -502,24 +502,27 @@ k_ball_query(const float* __restrict__ q, const int32_t* __restrict__ q_offs, co
     __shared__ int s_hits[BQ_WARPS][BQ_HCAP];
     __shared__ int s_sel[BQ_WARPS][BQ_KMAX];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * BQ_WARPS + warp;
-    if (slot >= nq_cap) return;
     const int nq = q_offs[n_clouds];
     const int ns = s_offs[n_clouds];
+    const float cell = hdr->cell;
+    const float r2 = __fmul_rn(radius, radius);
+    int* hits = s_hits[warp];
+    int* sel = s_sel[warp];
+    // persistent warps: a grid of a few CTAs per SM walks the query slots (the per-launch reads -- counts, cell size --
+    // and the CTA start-up are paid once per warp, not once per query)
+    for (int slot = blockIdx.x * BQ_WARPS + warp; slot < nq_cap; slot += gridDim.x * BQ_WARPS) {
     const int qi = q_order ? q_order[slot] : slot;
-    if (qi < 0 || qi >= nq_cap) return;
+    if (qi < 0 || qi >= nq_cap) continue;
     if (qi >= nq) {                            // capacity padding: a fully-shadow row, so that the
         for (int t = lane; t < K; t += 32) {   // whole (nq_cap, K) buffer is always initialised
             if (out32) out32[(long long)qi * K + t] = ns;
             if (out64) out64[(long long)qi * K + t] = ns;
         }
-        return;
+        continue;
     }
     const int c = regtr_cloud_of(q_offs, n_clouds, qi);
     const float qx = q[3 * qi + 0], qy = q[3 * qi + 1], qz = q[3 * qi + 2];
-    const float cell = hdr->cell;
     const int cx = regtr_cell_of(qx, cell), cy = regtr_cell_of(qy, cell), cz = regtr_cell_of(qz, cell);
-    const float r2 = __fmul_rn(radius, radius);
     // lanes 0..26: one cell of the 3x3x3 stencil each -> hash lookup of (start, count)
     int c_start = 0, c_cnt = 0;
     if (lane < 27) {
@@ -544,8 +547,6 @@ k_ball_query(const float* __restrict__ q, const int32_t* __restrict__ q_offs, co
         if (lane >= o) pre += v;
     }
     const int total = __shfl_sync(0xffffffffu, pre, 31);
-    int* hits = s_hits[warp];
-    int* sel = s_sel[warp];
     int count = 0;
     for (int base = 0; base < total; base += 32) {
         const int i = base + lane;
@@ -588,6 +589,8 @@ k_ball_query(const float* __restrict__ q, const int32_t* __restrict__ q_offs, co
         const int v = t < kept ? sel[t] : ns;
         if (out32) out32[row + t] = v;
         if (out64) out64[row + t] = v;
+    }
+    __syncwarp();                              // hits / sel are reused by the next query of this warp
     }
 }
 
@@ -838,7 +841,8 @@ int regtr_ball_query(const float* q, const int32_t* q_offs, const int32_t* q_ord
     const size_t n = s_cap > 0 ? (size_t)s_cap : 1;
     const float4* sxyzi = grid_sxyzi(const_cast<void*>(s_grid));
     const CellSlot* table = grid_table(const_cast<void*>(s_grid), n);
-    k_ball_query<<<regtr_cdiv(nq_cap, BQ_WARPS), BQ_WARPS * 32, 0, st>>>(
+    const int bq_blocks = regtr_cdiv(nq_cap, BQ_WARPS);
+    k_ball_query<<<bq_blocks < 8 * REGTR_NUM_SMS ? bq_blocks : 8 * REGTR_NUM_SMS, BQ_WARPS * 32, 0, st>>>(
         q, q_offs, q_order, s_offs, hdr, table, cell_table_log2(s_cap), sxyzi, n_clouds, nq_cap, K, radius, out_idx32,
         (long long*)out_idx64);
     REGTR_CHECK_LAUNCH();
