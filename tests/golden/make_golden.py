@@ -362,6 +362,45 @@ def loss_fixture():
     print('loss', {k: float(v) for k, v in fx.items() if k.startswith('loss_')})
 
 
+def grad_sample_index(name, numel, k=32):
+    """Deterministic sample positions of a parameter's gradient (shared with tests/test_oracle_grad.py)."""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    return np.sort(rng.choice(numel, size=min(k, numel), replace=False))
+
+
+def grad_fixture():
+    """d(total loss)/d(parameters) of the unmodified reference (eval mode: dropout off, autograd on) on the
+    `fwd_modelnet_b1` forward with the seeded loss inputs of loss_fixture: per parameter the l2 norm, the sum and 32
+    sampled entries.  Pins the ORACLE's backward (tests/test_oracle_grad.py) -- the checker a CUDA backward (SURVEY.md
+    8f N3) will be tested against."""
+    import eval_inputs as ei
+    cfg_name, wseed, makers = FORWARD_CASES['fwd_modelnet_b1'][:3]
+    cfg = get_config(cfg_name)
+    sd = ei.loss_state_dict(random_state_dict(cfg, wseed))
+    model = ref_bridge.build_reference_model(cfg, sd)
+    model.eval()
+    for p_ in model.parameters():
+        p_.requires_grad_(p_.is_floating_point())
+    pairs = [mk() for mk in makers]
+    batch = {'src_xyz': [torch.from_numpy(p['src_xyz']) for p in pairs], 'tgt_xyz': [torch.from_numpy(p['tgt_xyz']) for p in pairs]}
+    pred = model(batch)
+    batch.update(ei.loss_inputs(pairs, [int(x.shape[0]) for x in batch['src_xyz']], [int(x.shape[0]) for x in batch['tgt_xyz']]))
+    losses = model.compute_loss(pred, batch)
+    losses['total'].backward()
+    fx = {'loss_total': _np(losses['total'].detach())}
+    n = 0
+    for name, p_ in model.named_parameters():
+        if p_.grad is None:
+            continue
+        g = p_.grad.detach().double().reshape(-1)
+        idx = grad_sample_index(name, g.numel())
+        fx[f'g|{name}'] = np.concatenate([[float(g.norm()), float(g.sum())], g[torch.from_numpy(idx)].numpy()])
+        n += 1
+    np.savez_compressed(os.path.join(OUT, 'grad.npz'), **fx)
+    print('grad: parameters with a gradient', n, 'total loss', float(fx['loss_total']))
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     np.random.seed(0)
@@ -373,8 +412,12 @@ if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'bench':
         benchmark_fixture()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'grad':
+        grad_fixture()
+        sys.exit(0)
     eval_fixtures()
     loss_fixture()
+    grad_fixture()
     op_fixtures()
     for case in FORWARD_CASES:
         forward_fixture(case)
