@@ -107,3 +107,10 @@ def loss_inputs(pairs, src_lens, tgt_lens, seed=33):
     return {'pose': torch.from_numpy(pose),
             'src_overlap': [torch.from_numpy(rng.random(n) < 0.6) for n in src_lens],
             'tgt_overlap': [torch.from_numpy(rng.random(n) < 0.5) for n in tgt_lens]}
+
+
+def grad_sample_index(name, numel, k=32):
+    """Deterministic sample positions of a parameter's gradient (shared by make_golden.py:grad_fixture and tests/test_oracle_grad.py)."""
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    return np.sort(rng.choice(numel, size=min(k, numel), replace=False))

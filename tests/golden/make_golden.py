@@ -362,19 +362,13 @@ def loss_fixture():
     print('loss', {k: float(v) for k, v in fx.items() if k.startswith('loss_')})
 
 
-def grad_sample_index(name, numel, k=32):
-    """Deterministic sample positions of a parameter's gradient (shared with tests/test_oracle_grad.py)."""
-    import zlib
-    rng = np.random.default_rng(zlib.crc32(name.encode()))
-    return np.sort(rng.choice(numel, size=min(k, numel), replace=False))
-
-
 def grad_fixture():
     """d(total loss)/d(parameters) of the unmodified reference (eval mode: dropout off, autograd on) on the
     `fwd_modelnet_b1` forward with the seeded loss inputs of loss_fixture: per parameter the l2 norm, the sum and 32
     sampled entries.  Pins the ORACLE's backward (tests/test_oracle_grad.py) -- the checker a CUDA backward (SURVEY.md
     8f N3) will be tested against."""
     import eval_inputs as ei
+    grad_sample_index = ei.grad_sample_index
     cfg_name, wseed, makers = FORWARD_CASES['fwd_modelnet_b1'][:3]
     cfg = get_config(cfg_name)
     sd = ei.loss_state_dict(random_state_dict(cfg, wseed))
